@@ -1,0 +1,21 @@
+"""imageretrievalresearch_b200 — B200-native (sm_100a) retrieval-ranking hot path of
+vitasoftAI/ImageRetrievalResearch: cosine similarity -> top-k -> top1/top3 accounting and the
+contrastive / cosine-embedding losses, as hand-written CUDA kernels behind a C ABI
+(include/irr_b200.h, libirr_b200.so) with a torch-facing surface that mirrors the reference's calls.
+
+There is no CPU fallback: every function raises if the CUDA library is missing or the tensors are
+not on a CUDA device.
+"""
+from ._lib import IRR_MAX_K, IrrError, LIB_PATH, load as load_library
+from .losses import (ContrastiveLoss, CosineEmbeddingLoss, TripletFwdBwd, TripletLosses,
+                     triplet_losses, triplet_losses_fwd_bwd)
+from .retrieval import CosineSimilarity, Gallery, TopK, cosine_topk, top1_top3, topk_hits
+from .sharded import ShardedGallery, exchange_candidates, shard_bounds
+
+__all__ = [
+    "IRR_MAX_K", "IrrError", "LIB_PATH", "load_library",
+    "ContrastiveLoss", "CosineEmbeddingLoss", "TripletLosses", "TripletFwdBwd",
+    "triplet_losses", "triplet_losses_fwd_bwd",
+    "CosineSimilarity", "Gallery", "TopK", "cosine_topk", "top1_top3", "topk_hits",
+    "ShardedGallery", "exchange_candidates", "shard_bounds",
+]

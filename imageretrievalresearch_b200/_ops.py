@@ -1,0 +1,186 @@
+"""Tensor-level plumbing between torch and the C ABI: dtype/layout checks, stream and workspace
+handling.  PyTorch is used for device memory and streams only; all arithmetic is in csrc/."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import IRR_BF16, IRR_F32, IRR_MAX_K, IRR_ROW_STATS, check
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} is on {t.device}: the B200 retrieval-ranking path runs on CUDA only "
+            "(there is no CPU fallback)")
+
+
+def as_rows(t: torch.Tensor, name: str) -> torch.Tensor:
+    """[rows, D] contiguous fp32/bf16 CUDA tensor.  fp16 (autocast embeddings) is widened to fp32,
+    which is what the reference's autocast does for every reduction on this path."""
+    _require_cuda(t, name)
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D [rows, D], got shape {tuple(t.shape)}")
+    if t.dtype == torch.float16 or t.dtype == torch.float64:
+        t = t.float()
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"{name}: unsupported dtype {t.dtype}")
+    t = t.detach()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    return t
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    return IRR_BF16 if t.dtype == torch.bfloat16 else IRR_F32
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+_scratch: dict = {}
+_zeroed: dict = {}
+
+
+def scratch(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Reusable uninitialised workspace for the current (device, stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def zeroed_scratch(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Workspace that is zero-filled once (self-resetting sync words, see irr_b200.h)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _zeroed.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _zeroed[key] = buf
+    return buf
+
+
+def check_same(a: torch.Tensor, b: torch.Tensor, an: str, bn: str) -> None:
+    if a.device != b.device:
+        raise RuntimeError(f"{an} and {bn} are on different devices ({a.device} vs {b.device})")
+    if a.dtype != b.dtype:
+        raise TypeError(f"{an} and {bn} have different dtypes ({a.dtype} vs {b.dtype})")
+    if a.shape[1] != b.shape[1]:
+        raise RuntimeError(
+            f"embedding widths differ: {an} has D={a.shape[1]}, {bn} has D={b.shape[1]}")
+
+
+# -------------------------------------------------------------------------------------------------
+# thin typed calls
+# -------------------------------------------------------------------------------------------------
+def row_inv_norms(x: torch.Tensor, eps: float) -> torch.Tensor:
+    lib = _lib.load()
+    x = as_rows(x, "x")
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.irr_row_inv_norms(ptr(x), x.shape[0], x.shape[1], dtype_code(x), eps, ptr(out),
+                                    stream_ptr(x.device)), "irr_row_inv_norms")
+    return out
+
+
+def cosine_topk_raw(q: torch.Tensor, g: torch.Tensor, k: int, eps: float,
+                    g_inv_norm: Optional[torch.Tensor], idx_offset: int
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    Q, D = q.shape
+    N = g.shape[0]
+    dt = dtype_code(q)
+    vals = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+    with torch.cuda.device(q.device):
+        need = lib.irr_cosine_topk_workspace_bytes(Q, N, D, k, dt)
+        ws = scratch(q.device, need)
+        check(lib.irr_cosine_topk(ptr(q), ptr(g), ptr(g_inv_norm), Q, N, D, k, dt, eps, idx_offset,
+                                  ptr(vals), ptr(idx), ptr(ws), ws.numel(), stream_ptr(q.device)),
+              "irr_cosine_topk")
+    return vals, idx
+
+
+def cosine_scores_bf16(q: torch.Tensor, g: torch.Tensor, eps: float) -> torch.Tensor:
+    """Dense [Q,N] scores from the tensor-core kernel (test / bring-up aid)."""
+    lib = _lib.load()
+    q, g = as_rows(q, "q"), as_rows(g, "g")
+    check_same(q, g, "q", "g")
+    if q.dtype != torch.bfloat16:
+        raise TypeError("cosine_scores_bf16 needs bf16 inputs")
+    Q, D = q.shape
+    N = g.shape[0]
+    out = torch.empty((Q, N), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        ws = scratch(q.device, (N + Q) * 4 + 1024)
+        check(lib.irr_cosine_scores_bf16(ptr(q), ptr(g), Q, N, D, eps, ptr(out), ptr(ws),
+                                         ws.numel(), stream_ptr(q.device)),
+              "irr_cosine_scores_bf16")
+    return out
+
+
+def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[G,Q,k] candidate lists -> merged [Q,k]."""
+    lib = _lib.load()
+    _require_cuda(cand_val, "cand_val")
+    _require_cuda(cand_idx, "cand_idx")
+    if cand_val.dim() != 3 or cand_val.shape != cand_idx.shape:
+        raise ValueError("cand_val / cand_idx must both be [G, Q, k]")
+    cand_val = cand_val.contiguous().float()
+    cand_idx = cand_idx.contiguous().long()
+    G, Q, k = cand_val.shape
+    vals = torch.empty((Q, k), dtype=torch.float32, device=cand_val.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=cand_val.device)
+    with torch.cuda.device(cand_val.device):
+        check(lib.irr_topk_merge(ptr(cand_val), ptr(cand_idx), G, Q, k, ptr(vals), ptr(idx),
+                                 stream_ptr(cand_val.device)), "irr_topk_merge")
+    return vals, idx
+
+
+def topk_hits(idx: torch.Tensor, q_label: Optional[torch.Tensor], g_label: Optional[torch.Tensor],
+              instance_offset: int) -> torch.Tensor:
+    lib = _lib.load()
+    _require_cuda(idx, "indices")
+    idx = idx.contiguous().long()
+    Q, k = idx.shape
+    N = 0
+    if q_label is not None:
+        q_label = q_label.to(device=idx.device, dtype=torch.int64).contiguous()
+        g_label = g_label.to(device=idx.device, dtype=torch.int64).contiguous()
+        if q_label.numel() != Q:
+            raise ValueError(f"query_labels has {q_label.numel()} entries for {Q} queries")
+        N = g_label.numel()
+    out = torch.empty(2, dtype=torch.int64, device=idx.device)
+    with torch.cuda.device(idx.device):
+        check(lib.irr_topk_hits(ptr(idx), Q, k, ptr(q_label), ptr(g_label), N, instance_offset,
+                                ptr(out), stream_ptr(idx.device)), "irr_topk_hits")
+    return out
+
+
+def pair_cosine(x1: torch.Tensor, x2: torch.Tensor, eps: float) -> torch.Tensor:
+    lib = _lib.load()
+    N, D = x2.shape
+    out = torch.empty(N, dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        check(lib.irr_pair_cosine(ptr(x1), x1.shape[0], ptr(x2), N, D, dtype_code(x2), eps,
+                                  ptr(out), stream_ptr(x2.device)), "irr_pair_cosine")
+    return out
+
+
+def f32x4(vals) -> "C.Array":
+    return (C.c_float * 4)(*[float(v) for v in vals])
+
+
+__all__ = ["IRR_MAX_K", "IRR_ROW_STATS"]

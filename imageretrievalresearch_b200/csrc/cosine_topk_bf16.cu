@@ -1,0 +1,401 @@
+// cosine_topk_bf16.cu — K1: query x gallery cosine contraction on tcgen05 tensor cores with a
+// per-row top-k epilogue.  Replaces the reference's per-query
+//     sim = cos(q[i][None], G); vals, inds = torch.topk(sim, k)
+// loops (train/train_efficient_cos_con_ce_loss.py:270-281,374-392;
+// inference/training_analysis.ipynb:231-251) for all query rows in one launch.
+//
+// Layout / roles (one persistent CTA per SM, 256 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles of Q (128 x 64) and G (256 x 64),
+//               128-byte swizzle, into a 4-stage shared-memory ring (48 KB / stage)
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256, K=16) x4 per stage,
+//               fp32 accumulators in TMEM, two accumulator stages (2 x 256 of the 512 columns)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue: tcgen05.ld the accumulator (thread = query row, 32 columns at a time),
+//               scale by 1/max(|g|,eps), keep a running sorted top-k per row in registers.
+//               The Q x N scores never leave the SM.
+// Work unit = (query tile of 128 rows, chunk of consecutive 256-row gallery tiles); units are
+// numbered query-tile-fastest so that CTAs running at the same time share gallery tiles in L2.
+// Every unit writes a [128, k] partial list; topk_merge.cu folds the partials, applies
+// 1/max(|q|,eps) and widens the indices.
+#include <cuda.h>
+
+#include "irr_common.cuh"
+#include "irr_kernels.h"
+
+namespace irr {
+
+namespace {
+
+constexpr int BLOCK_M = 128;   // query rows per tile  (UMMA M)
+constexpr int BLOCK_N = 256;   // gallery rows per tile (UMMA N)
+constexpr int BLOCK_K = 64;    // bf16 elements per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_THREADS = 128;
+
+// dynamic shared memory carve-up (base aligned to 1024 B for the 128-byte swizzle)
+constexpr int SMEM_TILES = STAGES * STAGE_BYTES;                 // 196608
+constexpr int SMEM_GN = ACC_STAGES * BLOCK_N * 4;                // inverse gallery norms per tile
+constexpr int SMEM_BARS = (2 * STAGES + 2 * ACC_STAGES) * 8;
+constexpr int SMEM_TOTAL = SMEM_TILES + SMEM_GN + SMEM_BARS + 16;
+constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;                    // slack for manual alignment
+
+struct Plan {
+  int m_tiles, n_tiles, tiles_per_chunk, n_chunks, grid;
+};
+
+// Chunk the gallery tiles so that (query tiles x chunks) spreads evenly over the SMs.
+Plan make_plan(int64_t Q, int64_t N) {
+  Plan p;
+  const int sms = num_sms();
+  p.m_tiles = static_cast<int>((Q + BLOCK_M - 1) / BLOCK_M);
+  p.n_tiles = static_cast<int>((N + BLOCK_N - 1) / BLOCK_N);
+  if (p.m_tiles < 1) p.m_tiles = 1;
+  if (p.n_tiles < 1) p.n_tiles = 1;
+  // candidates: enough chunks that every SM gets work, few enough that partial lists stay small
+  int best_tpc = 1;
+  double best_cost = 1e300;
+  const int max_tpc = p.n_tiles < 64 ? p.n_tiles : 64;
+  for (int tpc = 1; tpc <= max_tpc; ++tpc) {
+    const int chunks = (p.n_tiles + tpc - 1) / tpc;
+    const long long units = 1ll * chunks * p.m_tiles;
+    const long long waves = (units + sms - 1) / sms;
+    // time ~ waves * tpc tiles (+ a per-unit start-up worth roughly a third of a tile)
+    const double cost = static_cast<double>(waves) * (tpc + 0.35);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best_tpc = tpc;
+    }
+  }
+  p.tiles_per_chunk = best_tpc;
+  p.n_chunks = (p.n_tiles + best_tpc - 1) / best_tpc;
+  const long long units = 1ll * p.n_chunks * p.m_tiles;
+  p.grid = static_cast<int>(units < sms ? units : sms);
+  return p;
+}
+
+template <int KMAX, bool WRITE_SCORES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                        const __grid_constant__ CUtensorMap tmap_g,
+                        const float* __restrict__ g_inv_norm, const float* __restrict__ q_inv_norm,
+                        int Q, int N, int num_kb, int k, int m_tiles, int n_tiles,
+                        int tiles_per_chunk, int n_chunks, float* __restrict__ part_val,
+                        int32_t* __restrict__ part_idx, float* __restrict__ scores_out,
+                        uint64_t g_policy) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t bars = smem_base + SMEM_TILES + SMEM_GN;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC_STAGES + s); };
+  const uint32_t tmem_slot = bars + SMEM_BARS;
+  float* gn_smem = reinterpret_cast<float*>(smem_gen + SMEM_TILES);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + SMEM_TILES + SMEM_GN + SMEM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_g);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), EPI_THREADS / 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int total_units = m_tiles * n_chunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int chunk = u / m_tiles, mt = u - chunk * m_tiles;
+      const int t0 = chunk * tiles_per_chunk;
+      const int t1 = min(t0 + tiles_per_chunk, n_tiles);
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
+          if (lane == 0) {
+            const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+            const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(a_dst, &tmap_q, kb * BLOCK_K, mt * BLOCK_M, full_bar(stage),
+                        kPolicyEvictLast);
+            tma_load_2d(b_dst, &tmap_g, kb * BLOCK_K, t * BLOCK_N, full_bar(stage), g_policy);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t it = 0;  // accumulator tiles issued by this CTA
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int chunk = u / m_tiles;
+      const int t0 = chunk * tiles_per_chunk;
+      const int t1 = min(t0 + tiles_per_chunk, n_tiles);
+      for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u, 200 + as);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, 300 + stage);
+          tcgen05_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+            const uint64_t adesc = umma_desc_k128(a_addr);
+            const uint64_t bdesc = umma_desc_k128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+              // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-byte units
+              umma_bf16_ss(tmem_d, adesc + 2u * kk, bdesc + 2u * kk, idesc,
+                           (kb > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));                 // frees the smem stage when MMAs finish
+            if (kb == num_kb - 1) umma_commit(tfull_bar(as));  // accumulator ready
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue: scale + running top-k =====================
+    const int ew = warp - EPI_WARP0;          // == warp % 4: TMEM lane quarter this warp may read
+    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
+    const int row_in_tile = ew * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+    TopKList<KMAX, int32_t> top;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int chunk = u / m_tiles, mt = u - chunk * m_tiles;
+      const int t0 = chunk * tiles_per_chunk;
+      const int t1 = min(t0 + tiles_per_chunk, n_tiles);
+      const int row = mt * BLOCK_M + row_in_tile;
+      top.reset();
+      float qn = 1.0f;
+      if (WRITE_SCORES && row < Q) qn = q_inv_norm[row];
+      for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        const int n0 = t * BLOCK_N;
+        float* gn = gn_smem + as * BLOCK_N;
+        {
+          const int c0 = n0 + et, c1 = n0 + et + EPI_THREADS;
+          gn[et] = c0 < N ? __ldg(g_inv_norm + c0) : 0.0f;
+          gn[et + EPI_THREADS] = c1 < N ? __ldg(g_inv_norm + c1) : 0.0f;
+        }
+        named_bar_sync(1, EPI_THREADS);
+        mbar_wait(tfull_bar(as), aphase, 400 + as);
+        tcgen05_fence_after();
+        const int n_valid = min(BLOCK_N, N - n0);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + lane_base + as * BLOCK_N + c, v);
+          tmem_ld_wait();
+          if (c >= n_valid) continue;  // warp-uniform
+          const float4* gn4 = reinterpret_cast<const float4*>(gn + c);
+          float mx = kNegInf;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = gn4[j];
+            v[4 * j + 0] *= g4.x; v[4 * j + 1] *= g4.y;
+            v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
+          }
+          if (WRITE_SCORES) {
+            if (row < Q) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c + j < n_valid)
+                  scores_out[static_cast<size_t>(row) * N + n0 + c + j] = v[j] * qn;
+            }
+          } else {
+            const bool full = c + 32 <= n_valid;
+            if (!full) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c + j >= n_valid) v[j] = kNegInf;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+            if (mx > top.v[KMAX - 1]) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) top.push_ordered(v[j], n0 + c + j);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
+      if (!WRITE_SCORES && row < Q) {
+        const size_t o = (static_cast<size_t>(chunk) * Q + row) * k;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          if (j < k) {
+            part_val[o + j] = top.v[j];
+            part_idx[o + j] = top.i[j];
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+            cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// [rows, cols] bf16 row-major, tile = box_rows x 64 columns, 128-byte swizzle, zero fill OOB
+bool encode_bf16_rows(CUtensorMap* m, const void* base, int64_t rows, int64_t cols,
+                      uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int KMAX, bool WS>
+irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, const float* qin,
+                  int64_t Q, int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
+                  float* scores, cudaStream_t st) {
+  auto kern = cosine_topk_bf16_kernel<KMAX, WS>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    attr_set = true;
+  }
+  const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
+  // a gallery streamed by a single query tile is read exactly once: do not let it displace the
+  // query tiles in L2; with several query tiles the gallery tiles are the L2-shared operand
+  const uint64_t g_policy = p.m_tiles == 1 ? kPolicyEvictFirst : kPolicyEvictNormal;
+  kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(tq, tg, gin, qin, static_cast<int>(Q),
+                                                static_cast<int>(N), num_kb, k, p.m_tiles,
+                                                p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
+                                                scores, g_policy);
+  IRR_LAUNCH_CHECK();
+  return IRR_OK;
+}
+
+}  // namespace
+
+// workspace: [g_inv_norm fp32 N][part_val fp32 chunks*Q*k][part_idx i32 chunks*Q*k]
+size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
+  const Plan p = make_plan(Q, N);
+  const size_t parts = static_cast<size_t>(p.n_chunks) * Q * k;
+  return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 + 256;
+}
+
+irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
+                            int64_t N, int32_t D, int32_t k, float eps, int64_t idx_offset,
+                            float* out_val, int64_t* out_idx, void* ws, size_t ws_bytes,
+                            cudaStream_t st) {
+  if (device_cc() / 10 != 10) return IRR_ERR_UNSUPPORTED_DEVICE;
+  if (N > 0x7fffff00ll || Q > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
+  if (ws_bytes < bf16_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
+  const Plan p = make_plan(Q, N);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  float* gin_ws = reinterpret_cast<float*>(w);
+  w += align_up(static_cast<size_t>(N) * 4, 256);
+  const size_t parts = static_cast<size_t>(p.n_chunks) * Q * k;
+  float* pv = reinterpret_cast<float*>(w);
+  w += align_up(parts * 4, 256);
+  int32_t* pi = reinterpret_cast<int32_t*>(w);
+
+  const float* gin = g_inv_norm;
+  if (!gin) {
+    irr_status s = row_inv_norms(g, N, D, IRR_BF16, eps, gin_ws, st);
+    if (s != IRR_OK) return s;
+    gin = gin_ws;
+  }
+  CUtensorMap tq, tg;
+  if (!encode_bf16_rows(&tq, q, Q, D, BLOCK_M) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
+    return IRR_ERR_UNSUPPORTED_DEVICE;
+  irr_status s;
+  if (k <= 4)
+    s = launch<4, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, st);
+  else
+    s = launch<16, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, st);
+  if (s != IRR_OK) return s;
+  return merge_partials(pv, pi, p.n_chunks, Q, k, q, D, IRR_BF16, eps, idx_offset, out_val, out_idx,
+                        st);
+}
+
+irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N, int32_t D,
+                              float eps, float* out_scores, void* ws, size_t ws_bytes,
+                              cudaStream_t st) {
+  if (device_cc() / 10 != 10) return IRR_ERR_UNSUPPORTED_DEVICE;
+  if (N > 0x7fffff00ll || Q > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
+  const size_t need = align_up(static_cast<size_t>(N) * 4, 256) + align_up(static_cast<size_t>(Q) * 4, 256);
+  if (ws_bytes < need) return IRR_ERR_WORKSPACE_TOO_SMALL;
+  float* gin = static_cast<float*>(ws);
+  float* qin = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + align_up(static_cast<size_t>(N) * 4, 256));
+  irr_status s = row_inv_norms(g, N, D, IRR_BF16, eps, gin, st);
+  if (s != IRR_OK) return s;
+  s = row_inv_norms(q, Q, D, IRR_BF16, eps, qin, st);
+  if (s != IRR_OK) return s;
+  const Plan p = make_plan(Q, N);
+  CUtensorMap tq, tg;
+  if (!encode_bf16_rows(&tq, q, Q, D, BLOCK_M) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
+    return IRR_ERR_UNSUPPORTED_DEVICE;
+  return launch<4, true>(tq, tg, gin, qin, Q, N, D, 1, p, nullptr, nullptr, out_scores, st);
+}
+
+}  // namespace irr

@@ -1,0 +1,227 @@
+// cosine_topk_f32.cu — K1 exactness path: fp32 inputs, FFMA accumulation (tensor cores cannot hold
+// the 1e-5-relative bar of the fp32 mode: kind::tf32 keeps 10 mantissa bits), same running top-k
+// and tie rule as the bf16 tensor-core kernel.  Replaces cos(q[i][None], G) + torch.topk(sim, k)
+// (train/train_efficient_cos_con_ce_loss.py:273-276,385-388; ipynb:238) for fp32 embeddings.
+//
+// CTA = 256 threads, score tile 64 queries x 128 gallery rows, K-slabs of 16 staged transposed in
+// shared memory with register prefetch; each thread owns a 4 x 8 register micro-tile.  The scaled
+// tile goes to shared memory once, and 64 threads (one per query row) fold it into their running
+// sorted top-k in increasing column order.  Work unit = (query tile, chunk of gallery tiles); the
+// per-unit partial lists are folded by topk_merge.cu.
+#include "irr_common.cuh"
+#include "irr_kernels.h"
+
+namespace irr {
+namespace {
+
+constexpr int BM = 64, BN = 128, BK = 16;
+constexpr int THREADS = 256;
+constexpr int A_LD = BM + 4, B_LD = BN + 4, S_LD = BN + 1;
+constexpr int SMEM_A = 2 * BK * A_LD * 4;
+constexpr int SMEM_B = 2 * BK * B_LD * 4;
+constexpr int SMEM_S = BM * S_LD * 4;
+constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_S;
+
+struct Plan {
+  int m_tiles, n_tiles, tiles_per_chunk, n_chunks;
+};
+
+Plan make_plan(int64_t Q, int64_t N) {
+  Plan p;
+  p.m_tiles = static_cast<int>((Q + BM - 1) / BM);
+  p.n_tiles = static_cast<int>((N + BN - 1) / BN);
+  if (p.m_tiles < 1) p.m_tiles = 1;
+  if (p.n_tiles < 1) p.n_tiles = 1;
+  const int slots = num_sms() * 2;  // two resident CTAs per SM
+  int best = 1;
+  double best_cost = 1e300;
+  const int max_tpc = p.n_tiles < 64 ? p.n_tiles : 64;
+  for (int tpc = 1; tpc <= max_tpc; ++tpc) {
+    const long long units = 1ll * ((p.n_tiles + tpc - 1) / tpc) * p.m_tiles;
+    const long long waves = (units + slots - 1) / slots;
+    const double cost = static_cast<double>(waves) * (tpc + 0.1);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = tpc; }
+  }
+  p.tiles_per_chunk = best;
+  p.n_chunks = (p.n_tiles + best - 1) / best;
+  return p;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(THREADS, 2)
+cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
+                       const float* __restrict__ g_inv_norm, int Q, int N, int D, int k,
+                       int m_tiles, int n_tiles, int tiles_per_chunk,
+                       float* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float* As = reinterpret_cast<float*>(smem);                      // [2][BK][A_LD]
+  float* Bs = reinterpret_cast<float*>(smem + SMEM_A);             // [2][BK][B_LD]
+  float* Ss = reinterpret_cast<float*>(smem + SMEM_A + SMEM_B);    // [BM][S_LD]
+
+  const int t = threadIdx.x;
+  const int ty = t >> 4, tx = t & 15;
+  const int chunk = blockIdx.x / m_tiles, mt = blockIdx.x - chunk * m_tiles;
+  const int m0 = mt * BM;
+  const int t0 = chunk * tiles_per_chunk, t1 = min(t0 + tiles_per_chunk, n_tiles);
+
+  // global -> smem staging assignment: A: one float4 / thread, B: two float4 / thread
+  const int a_row = t >> 2, a_kq = (t & 3) * 4;
+  const bool a_ok = m0 + a_row < Q;
+  const float* a_src = q + static_cast<size_t>(a_ok ? m0 + a_row : 0) * D + a_kq;
+
+  TopKList<KMAX, int32_t> top;
+  top.reset();
+
+  const int num_ks = (D + BK - 1) / BK;
+  for (int tile = t0; tile < t1; ++tile) {
+    const int n0 = tile * BN;
+    const float* b_src[2];
+    bool b_ok[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = t + i * THREADS;
+      const int row = f >> 2;
+      b_ok[i] = n0 + row < N;
+      b_src[i] = g + static_cast<size_t>(b_ok[i] ? n0 + row : 0) * D + (f & 3) * 4;
+    }
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float4 ra, rb[2];
+    auto gload = [&](int ks) {
+      const int kk = ks * BK;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      ra = (a_ok && kk + a_kq < D) ? __ldg(reinterpret_cast<const float4*>(a_src + kk)) : z;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int kq = ((t + i * THREADS) & 3) * 4;
+        rb[i] = (b_ok[i] && kk + kq < D) ? __ldg(reinterpret_cast<const float4*>(b_src[i] + kk)) : z;
+      }
+    };
+    auto sstore = [&](int buf) {
+      float* a = As + buf * BK * A_LD;
+      a[(a_kq + 0) * A_LD + a_row] = ra.x;
+      a[(a_kq + 1) * A_LD + a_row] = ra.y;
+      a[(a_kq + 2) * A_LD + a_row] = ra.z;
+      a[(a_kq + 3) * A_LD + a_row] = ra.w;
+      float* b = Bs + buf * BK * B_LD;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int f = t + i * THREADS;
+        const int row = f >> 2, kq = (f & 3) * 4;
+        b[(kq + 0) * B_LD + row] = rb[i].x;
+        b[(kq + 1) * B_LD + row] = rb[i].y;
+        b[(kq + 2) * B_LD + row] = rb[i].z;
+        b[(kq + 3) * B_LD + row] = rb[i].w;
+      }
+    };
+
+    gload(0);
+    __syncthreads();  // previous tile's readers of As/Bs/Ss are done
+    sstore(0);
+    __syncthreads();
+    for (int ks = 0; ks < num_ks; ++ks) {
+      const int buf = ks & 1;
+      if (ks + 1 < num_ks) gload(ks + 1);
+      const float* a = As + buf * BK * A_LD + ty * 4;
+      const float* b = Bs + buf * BK * B_LD + tx * 4;
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 av = *reinterpret_cast<const float4*>(a + kk * A_LD);
+        const float4 b0 = *reinterpret_cast<const float4*>(b + kk * B_LD);
+        const float4 b1 = *reinterpret_cast<const float4*>(b + kk * B_LD + 64);
+        const float ar[4] = {av.x, av.y, av.z, av.w};
+        const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+      if (ks + 1 < num_ks) {
+        sstore(buf ^ 1);  // the other buffer was last read one iteration ago, before the sync below
+        __syncthreads();
+      }
+    }
+    // scale by the inverse gallery norms and publish the tile
+    float gn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      gn[j] = c < N ? __ldg(g_inv_norm + c) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4);
+        Ss[(ty * 4 + i) * S_LD + c] = acc[i][j] * gn[j];
+      }
+    __syncthreads();
+    if (t < BM) {
+      const int n_valid = min(BN, N - n0);
+      const float* s = Ss + t * S_LD;
+      for (int c = 0; c < n_valid; ++c) top.push_ordered(s[c], n0 + c);
+    }
+  }
+  if (t < BM && m0 + t < Q) {
+    const size_t o = (static_cast<size_t>(chunk) * Q + m0 + t) * k;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j < k) {
+        part_val[o + j] = top.v[j];
+        part_idx[o + j] = top.i[j];
+      }
+  }
+}
+
+}  // namespace
+
+size_t f32_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
+  const Plan p = make_plan(Q, N);
+  const size_t parts = static_cast<size_t>(p.n_chunks) * Q * k;
+  return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 + 256;
+}
+
+irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
+                           int64_t N, int32_t D, int32_t k, float eps, int64_t idx_offset,
+                           float* out_val, int64_t* out_idx, void* ws, size_t ws_bytes,
+                           cudaStream_t st) {
+  if (N > 0x7fffff00ll || Q > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
+  if (ws_bytes < f32_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
+  const Plan p = make_plan(Q, N);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  float* gin_ws = reinterpret_cast<float*>(w);
+  w += align_up(static_cast<size_t>(N) * 4, 256);
+  const size_t parts = static_cast<size_t>(p.n_chunks) * Q * k;
+  float* pv = reinterpret_cast<float*>(w);
+  w += align_up(parts * 4, 256);
+  int32_t* pi = reinterpret_cast<int32_t*>(w);
+
+  const float* gin = g_inv_norm;
+  if (!gin) {
+    irr_status s = row_inv_norms(g, N, D, IRR_F32, eps, gin_ws, st);
+    if (s != IRR_OK) return s;
+    gin = gin_ws;
+  }
+  const int grid = p.m_tiles * p.n_chunks;
+  if (k <= 4) {
+    auto kern = cosine_topk_f32_kernel<4>;
+    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(static_cast<const float*>(q), static_cast<const float*>(g),
+                                            gin, static_cast<int>(Q), static_cast<int>(N), D, k,
+                                            p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi);
+  } else {
+    auto kern = cosine_topk_f32_kernel<16>;
+    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(static_cast<const float*>(q), static_cast<const float*>(g),
+                                            gin, static_cast<int>(Q), static_cast<int>(N), D, k,
+                                            p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi);
+  }
+  IRR_LAUNCH_CHECK();
+  return merge_partials(pv, pi, p.n_chunks, Q, k, q, D, IRR_F32, eps, idx_offset, out_val, out_idx, st);
+}
+
+}  // namespace irr

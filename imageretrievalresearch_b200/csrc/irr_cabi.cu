@@ -1,0 +1,251 @@
+// irr_cabi.cu — the extern "C" boundary declared in include/irr_b200.h: argument validation and
+// dispatch to the kernels.  Nothing here allocates, synchronises or falls back to the host.
+#include "irr_common.cuh"
+#include "irr_kernels.h"
+
+namespace irr {
+
+int num_sms() {
+  static int cached = []() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return 148;
+    }
+    return n;
+  }();
+  return cached;
+}
+
+int device_cc() {
+  static int cached = []() {
+    int dev = 0, mj = 0, mn = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&mn, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    return mj * 10 + mn;
+  }();
+  return cached;
+}
+
+namespace {
+
+irr_status check_rows(const void* p, int32_t D, irr_dtype dt) {
+  if (dt != IRR_F32 && dt != IRR_BF16) return IRR_ERR_UNSUPPORTED_DTYPE;
+  if (D <= 0) return IRR_ERR_INVALID_ARG;
+  if ((D * dtype_bytes(dt)) % 16 != 0) return IRR_ERR_ALIGNMENT;
+  if (p && !aligned16(p)) return IRR_ERR_ALIGNMENT;
+  return IRR_OK;
+}
+
+}  // namespace
+}  // namespace irr
+
+using namespace irr;
+
+extern "C" {
+
+int32_t irr_version(void) { return 100; }
+
+const char* irr_status_string(irr_status s) {
+  switch (s) {
+    case IRR_OK: return "ok";
+    case IRR_ERR_INVALID_ARG: return "invalid argument";
+    case IRR_ERR_UNSUPPORTED_DTYPE: return "unsupported dtype";
+    case IRR_ERR_ALIGNMENT: return "pointer or row length violates the 16-byte alignment contract";
+    case IRR_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case IRR_ERR_K_TOO_LARGE: return "k exceeds IRR_MAX_K";
+    case IRR_ERR_UNSUPPORTED_DEVICE: return "device is not sm_100 or the driver lacks tensor maps";
+    case IRR_ERR_ROW_TOO_LONG: return "row too long for the shared-memory staged loss kernel";
+    default: return s > 0 ? cudaGetErrorString(static_cast<cudaError_t>(s)) : "unknown status";
+  }
+}
+
+size_t irr_cosine_topk_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t k, irr_dtype dt) {
+  (void)D;
+  if (Q < 0 || N < 0 || k < 1) return 0;
+  return dt == IRR_BF16 ? bf16_topk_workspace_bytes(Q, N, k) : f32_topk_workspace_bytes(Q, N, k);
+}
+
+irr_status irr_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
+                           int64_t N, int32_t D, int32_t k, irr_dtype dt, float eps,
+                           int64_t idx_offset, float* out_val, int64_t* out_idx, void* workspace,
+                           size_t workspace_bytes, irr_stream_t stream) {
+  if (Q < 0 || N < 0 || k < 1 || !out_val || !out_idx) return IRR_ERR_INVALID_ARG;
+  if (k > IRR_MAX_K) return IRR_ERR_K_TOO_LARGE;
+  if (Q == 0) return IRR_OK;
+  if (!q || (N > 0 && !g) || !workspace) return IRR_ERR_INVALID_ARG;
+  irr_status s = check_rows(q, D, dt);
+  if (s != IRR_OK) return s;
+  s = check_rows(g, D, dt);
+  if (s != IRR_OK) return s;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dt == IRR_BF16)
+    return bf16_cosine_topk(q, g, g_inv_norm, Q, N, D, k, eps, idx_offset, out_val, out_idx,
+                            workspace, workspace_bytes, st);
+  return f32_cosine_topk(q, g, g_inv_norm, Q, N, D, k, eps, idx_offset, out_val, out_idx, workspace,
+                         workspace_bytes, st);
+}
+
+irr_status irr_cosine_scores_bf16(const void* q, const void* g, int64_t Q, int64_t N, int32_t D,
+                                  float eps, float* out_scores, void* workspace,
+                                  size_t workspace_bytes, irr_stream_t stream) {
+  if (Q <= 0 || N <= 0 || !q || !g || !out_scores || !workspace) return IRR_ERR_INVALID_ARG;
+  irr_status s = check_rows(q, D, IRR_BF16);
+  if (s != IRR_OK) return s;
+  s = check_rows(g, D, IRR_BF16);
+  if (s != IRR_OK) return s;
+  return bf16_cosine_scores(q, g, Q, N, D, eps, out_scores, workspace, workspace_bytes,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_row_inv_norms(const void* x, int64_t N, int32_t D, irr_dtype dt, float eps,
+                             float* out, irr_stream_t stream) {
+  if (N < 0 || (N > 0 && (!x || !out))) return IRR_ERR_INVALID_ARG;
+  irr_status s = check_rows(x, D, dt);
+  if (s != IRR_OK) return s;
+  return row_inv_norms(x, N, D, dt, eps, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_topk_merge(const float* cand_val, const int64_t* cand_idx, int32_t G, int64_t Q,
+                          int32_t k, float* out_val, int64_t* out_idx, irr_stream_t stream) {
+  if (G < 1 || Q < 0 || k < 1 || !cand_val || !cand_idx || !out_val || !out_idx)
+    return IRR_ERR_INVALID_ARG;
+  if (k > IRR_MAX_K) return IRR_ERR_K_TOO_LARGE;
+  return merge_candidates(cand_val, cand_idx, G, Q, k, out_val, out_idx,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_topk_hits(const int64_t* idx, int64_t Q, int32_t k, const int64_t* q_label,
+                         const int64_t* g_label, int64_t N, int64_t instance_offset,
+                         int64_t* out_hits, irr_stream_t stream) {
+  if (Q < 0 || k < 1 || !out_hits || (Q > 0 && !idx)) return IRR_ERR_INVALID_ARG;
+  if ((q_label == nullptr) != (g_label == nullptr)) return IRR_ERR_INVALID_ARG;
+  return topk_hits(idx, Q, k, q_label, g_label, N, instance_offset, out_hits,
+                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_pair_cosine(const void* x1, int64_t x1_rows, const void* x2, int64_t N, int32_t D,
+                           irr_dtype dt, float eps, float* out, irr_stream_t stream) {
+  if (N < 0 || (x1_rows != N && x1_rows != 1)) return IRR_ERR_INVALID_ARG;
+  if (N > 0 && (!x1 || !x2 || !out)) return IRR_ERR_INVALID_ARG;
+  irr_status s = check_rows(x1, D, dt);
+  if (s != IRR_OK) return s;
+  s = check_rows(x2, D, dt);
+  if (s != IRR_OK) return s;
+  return pair_cosine(x1, x1_rows, x2, N, D, dt, eps, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t irr_triplet_loss_workspace_bytes(int64_t B, int32_t D, irr_dtype dt) {
+  return loss_workspace_bytes(B, D, dt);
+}
+size_t irr_pair_loss_workspace_bytes(int64_t B, int32_t D, irr_dtype dt) {
+  return loss_workspace_bytes(B, D, dt);
+}
+
+irr_status irr_triplet_loss_fwd_bwd(const void* q, const void* p, const void* n, int64_t B,
+                                    int32_t D, irr_dtype dt, float margin_cos, float margin_con,
+                                    int32_t reduce_mean, float pair_eps, float* losses,
+                                    float* pair_cos, float* row_stats, void* dq, void* dp, void* dn,
+                                    const float grad_scale[4], void* workspace,
+                                    size_t workspace_bytes, irr_stream_t stream) {
+  if (B <= 0 || !q || !p || !n || !losses || !workspace) return IRR_ERR_INVALID_ARG;
+  const int ng = (dq != nullptr) + (dp != nullptr) + (dn != nullptr);
+  if (ng != 0 && ng != 3) return IRR_ERR_INVALID_ARG;
+  const void* ptrs[6] = {q, p, n, dq, dp, dn};
+  for (const void* x : ptrs) {
+    irr_status s = check_rows(x, D, dt);
+    if (s != IRR_OK) return s;
+  }
+  if (row_stats && !aligned16(row_stats)) return IRR_ERR_ALIGNMENT;
+  LossArgs a = {};
+  a.q = q; a.p = p; a.n = n;
+  a.B = B; a.D = D; a.dt = dt;
+  a.margin_cos = margin_cos; a.margin_con = margin_con;
+  a.reduce_mean = reduce_mean; a.pair_eps = pair_eps;
+  a.losses = losses; a.pair_cos = pair_cos; a.row_stats = row_stats;
+  a.dq = dq; a.dp = dp; a.dn = dn;
+  for (int j = 0; j < 4; ++j) a.grad_scale[j] = grad_scale ? grad_scale[j] : 1.0f;
+  return loss_fwd_bwd(a, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_triplet_loss_bwd(const void* q, const void* p, const void* n,
+                                const float* row_stats, const float* grad_out, int64_t B, int32_t D,
+                                irr_dtype dt, float margin_cos, float margin_con,
+                                int32_t reduce_mean, void* dq, void* dp, void* dn,
+                                irr_stream_t stream) {
+  if (B <= 0 || !q || !p || !n || !row_stats || !grad_out || !dq || !dp || !dn)
+    return IRR_ERR_INVALID_ARG;
+  const void* ptrs[6] = {q, p, n, dq, dp, dn};
+  for (const void* x : ptrs) {
+    irr_status s = check_rows(x, D, dt);
+    if (s != IRR_OK) return s;
+  }
+  if (!aligned16(row_stats)) return IRR_ERR_ALIGNMENT;
+  LossArgs a = {};
+  a.q = q; a.p = p; a.n = n;
+  a.B = B; a.D = D; a.dt = dt;
+  a.margin_cos = margin_cos; a.margin_con = margin_con;
+  a.reduce_mean = reduce_mean;
+  a.row_stats = const_cast<float*>(row_stats);
+  a.dq = dq; a.dp = dp; a.dn = dn;
+  return loss_bwd(a, grad_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_pair_loss_fwd_bwd(const void* a_, const void* b_, const float* label,
+                                 int64_t label_count, int64_t B, int32_t D, irr_dtype dt,
+                                 int32_t kind, float margin, int32_t reduce_mean, float* loss,
+                                 float* row_stats, void* da, void* db, float grad_scale,
+                                 void* workspace, size_t workspace_bytes, irr_stream_t stream) {
+  if (B <= 0 || !a_ || !b_ || !label || !loss || !workspace) return IRR_ERR_INVALID_ARG;
+  if (label_count != 1 && label_count != B) return IRR_ERR_INVALID_ARG;
+  if (kind != IRR_LOSS_CONTRASTIVE && kind != IRR_LOSS_COSINE_EMBEDDING) return IRR_ERR_INVALID_ARG;
+  if ((da != nullptr) != (db != nullptr)) return IRR_ERR_INVALID_ARG;
+  const void* ptrs[4] = {a_, b_, da, db};
+  for (const void* x : ptrs) {
+    irr_status s = check_rows(x, D, dt);
+    if (s != IRR_OK) return s;
+  }
+  if (row_stats && !aligned16(row_stats)) return IRR_ERR_ALIGNMENT;
+  LossArgs a = {};
+  a.q = a_; a.p = b_; a.n = nullptr;
+  a.label = label; a.label_count = label_count;
+  a.B = B; a.D = D; a.dt = dt; a.kind = kind;
+  a.margin_cos = margin; a.margin_con = margin;
+  a.reduce_mean = reduce_mean; a.pair_eps = 1e-6f;
+  a.losses = loss; a.row_stats = row_stats;
+  a.dq = da; a.dp = db;
+  a.grad_scale[0] = grad_scale;
+  return loss_fwd_bwd(a, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_pair_loss_bwd(const void* a_, const void* b_, const float* label,
+                             int64_t label_count, const float* row_stats, const float* grad_out,
+                             int64_t B, int32_t D, irr_dtype dt, int32_t kind, float margin,
+                             int32_t reduce_mean, void* da, void* db, irr_stream_t stream) {
+  if (B <= 0 || !a_ || !b_ || !label || !row_stats || !grad_out || !da || !db)
+    return IRR_ERR_INVALID_ARG;
+  if (label_count != 1 && label_count != B) return IRR_ERR_INVALID_ARG;
+  if (kind != IRR_LOSS_CONTRASTIVE && kind != IRR_LOSS_COSINE_EMBEDDING) return IRR_ERR_INVALID_ARG;
+  const void* ptrs[4] = {a_, b_, da, db};
+  for (const void* x : ptrs) {
+    irr_status s = check_rows(x, D, dt);
+    if (s != IRR_OK) return s;
+  }
+  if (!aligned16(row_stats)) return IRR_ERR_ALIGNMENT;
+  LossArgs a = {};
+  a.q = a_; a.p = b_; a.n = nullptr;
+  a.label = label; a.label_count = label_count;
+  a.B = B; a.D = D; a.dt = dt; a.kind = kind;
+  a.margin_cos = margin; a.margin_con = margin;
+  a.reduce_mean = reduce_mean;
+  a.row_stats = const_cast<float*>(row_stats);
+  a.dq = da; a.dp = db;
+  return loss_bwd(a, grad_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+"""Retrieval-ranking surface: the same calls the reference makes, fused and batched.
+
+Reference call sites this module stands in for (paths under the reference tree):
+  cos = CosineSimilarity(dim=1, eps=1e-6)            train/train_efficient_cos_con_ce_loss.py:89
+  sim = cos(fm_ims[idx].unsqueeze(0), fm_poss)       :273, :385       ipynb:238
+  vals, inds = torch.topk(sim, k=3)                  :276, :388       inference/inference.py:235,240
+  top3 / top1 class tests                            :279-281, :390-392
+  instance tests  len(inds[idx == inds])             inference/inference.py:237,242
+  paired scores cos(q[i][None], p[i][None])          :377, :381       ipynb:232,234
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional, Tuple
+
+import torch
+
+from . import _ops
+from ._lib import IRR_MAX_K
+
+
+class TopK(NamedTuple):
+    values: torch.Tensor   # [Q, k] fp32, descending
+    indices: torch.Tensor  # [Q, k] int64, ties -> lower gallery index
+
+
+class CosineSimilarity(torch.nn.Module):
+    """Drop-in for ``torch.nn.CosineSimilarity(dim=1, eps)`` on 2-D embeddings.
+
+    ``forward(x1, x2)`` accepts the two shapes the reference uses: row-wise pairs ``[N,D] x [N,D]``
+    and one query against a gallery ``[1,D]`` / ``[D]`` x ``[N,D]``; returns ``[N]`` fp32.
+    Evaluation-only (the reference uses it for metrics): the result carries no autograd graph.
+    """
+
+    def __init__(self, dim: int = 1, eps: float = 1e-8) -> None:
+        super().__init__()
+        if dim not in (1, -1):
+            raise ValueError("only dim=1 (the embedding axis of [rows, D]) is supported")
+        self.dim, self.eps = dim, eps
+
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+        if x1.dim() == 1:
+            x1 = x1.unsqueeze(0)
+        if x2.dim() == 1:
+            x2 = x2.unsqueeze(0)
+        if x2.shape[0] == 1 and x1.shape[0] != 1:
+            x1, x2 = x2, x1  # cosine is symmetric
+        a, b = _ops.as_rows(x1, "x1"), _ops.as_rows(x2, "x2")
+        _ops.check_same(a, b, "x1", "x2")
+        if a.shape[0] not in (1, b.shape[0]):
+            raise RuntimeError(
+                f"The size of tensor a ({a.shape[0]}) must match the size of tensor b "
+                f"({b.shape[0]}) at non-singleton dimension 0")
+        return _ops.pair_cosine(a, b, self.eps)
+
+
+def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, eps: float = 1e-6, *,
+                gallery_inv_norm: Optional[torch.Tensor] = None, idx_offset: int = 0,
+                allow_short: bool = False) -> TopK:
+    """Fused ``topk(cos(q_i[None], gallery), k)`` for every query row.
+
+    Row ``i`` of the result is what the reference's per-query loop yields for query ``i``:
+    values sorted descending, int64 indices; ties resolve to the lower gallery index (torch.topk
+    leaves tie order unspecified).  fp32 inputs take the exact FFMA path, bf16 inputs the
+    tcgen05 tensor-core path; both accumulate and emit fp32.  The Q x N score matrix is never
+    materialised.
+
+    gallery_inv_norm: cached ``1/max(|g|, eps)`` per gallery row (see :class:`Gallery`).
+    idx_offset: added to the returned indices (first row of this shard).
+    allow_short: a shard with fewer than ``k`` rows pads with (-inf, -1) instead of raising.
+    """
+    q, g = _ops.as_rows(queries, "queries"), _ops.as_rows(gallery, "gallery")
+    _ops.check_same(q, g, "queries", "gallery")
+    if not isinstance(k, int) or k < 1:
+        raise ValueError(f"k must be a positive int, got {k!r}")
+    if k > IRR_MAX_K:
+        raise ValueError(f"k={k} exceeds the supported maximum of {IRR_MAX_K}")
+    if k > g.shape[0] and not allow_short:
+        raise RuntimeError("selected index k out of range")  # torch.topk's message
+    if gallery_inv_norm is not None:
+        gallery_inv_norm = gallery_inv_norm.to(device=g.device, dtype=torch.float32).contiguous()
+        if gallery_inv_norm.numel() != g.shape[0]:
+            raise ValueError("gallery_inv_norm must have one entry per gallery row")
+    vals, idx = _ops.cosine_topk_raw(q, g, k, eps, gallery_inv_norm, idx_offset)
+    return TopK(vals, idx)
+
+
+def topk_hits(indices: torch.Tensor, query_labels: Optional[torch.Tensor] = None,
+              gallery_labels: Optional[torch.Tensor] = None, instance_offset: int = 0
+              ) -> torch.Tensor:
+    """int64[2] = (#queries hit at rank 1, #queries hit anywhere in the k columns), on the device.
+
+    class flavour (labels given): hit when ``query_labels[i] == gallery_labels[indices[i, j]]``
+    (train/train_efficient_cos_con_ce_loss.py:279-281); instance flavour (no labels): hit when
+    ``indices[i, j] == i + instance_offset`` (inference/inference.py:237,242).
+    """
+    if (query_labels is None) != (gallery_labels is None):
+        raise ValueError("give both query_labels and gallery_labels, or neither")
+    return _ops.topk_hits(indices, query_labels, gallery_labels, instance_offset)
+
+
+def top1_top3(queries: torch.Tensor, gallery: torch.Tensor,
+              query_labels: Optional[torch.Tensor] = None,
+              gallery_labels: Optional[torch.Tensor] = None, *, k: int = 3, eps: float = 1e-6
+              ) -> Tuple[torch.Tensor, torch.Tensor, TopK]:
+    """The whole evaluation loop of training_step / validation_step in three launches.
+
+    Returns (top1, topk) as 0-d fp32 device tensors holding hits / Q — the quantities the reference
+    logs as ``train_top1`` / ``train_top3`` — plus the TopK lists.  No host synchronisation.
+    """
+    res = cosine_topk(queries, gallery, k, eps)
+    hits = topk_hits(res.indices, query_labels, gallery_labels)
+    frac = hits.to(torch.float32) / float(res.indices.shape[0])
+    return frac[0], frac[1], res
+
+
+class Gallery:
+    """A resident gallery shard: embeddings plus cached inverse row norms.
+
+    The reference re-normalises the whole gallery for every query
+    (train/train_efficient_cos_con_ce_loss.py:273 inside the ``for idx`` loop); a gallery that is
+    searched more than once caches ``1/max(|g|, eps)`` instead.
+    """
+
+    def __init__(self, embeddings: torch.Tensor, eps: float = 1e-6, first_row: int = 0,
+                 cache_norms: bool = True) -> None:
+        self.embeddings = _ops.as_rows(embeddings, "embeddings")
+        self.eps = eps
+        self.first_row = int(first_row)
+        self.inv_norm = _ops.row_inv_norms(self.embeddings, eps) if cache_norms else None
+
+    @property
+    def num_rows(self) -> int:
+        return self.embeddings.shape[0]
+
+    def search(self, queries: torch.Tensor, k: int, allow_short: bool = False) -> TopK:
+        return cosine_topk(queries, self.embeddings, k, self.eps, gallery_inv_norm=self.inv_norm,
+                           idx_offset=self.first_row, allow_short=allow_short)

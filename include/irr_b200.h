@@ -1,0 +1,199 @@
+/*
+ * irr_b200.h — C ABI of the B200-native retrieval-ranking hot path.
+ *
+ * This is the drop-in boundary for the similarity / top-k / embedding-loss path of
+ * vitasoftAI/ImageRetrievalResearch.  The reference has no FFI: its "interface" for this path is
+ * four torch calls made from Python.  Every entry point below names the reference
+ * call site(s) it replaces as file:line under the reference tree.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - return irr_status: 0 = OK, negative = argument / capability error detected on the host
+ *     before anything is enqueued, positive = a cudaError_t passed through unchanged.
+ *   - all pointers except `losses_host`-style out-params documented as host are DEVICE pointers
+ *     owned by the caller; outputs and workspaces are caller-allocated; the library never
+ *     allocates or frees device memory and never synchronises the device: work is enqueued on
+ *     `stream` and the call returns.
+ *   - a `*_workspace_bytes` query sizes the scratch buffer of the matching call.  Workspaces of
+ *     the loss entry points start with self-resetting sync words: the buffer must be zero-filled
+ *     ONCE before its first use and may then be reused by any number of calls on one stream.
+ *   - row-major contiguous embeddings, row stride == D elements; base pointers 16-byte aligned;
+ *     D % 8 == 0 for IRR_BF16 and D % 4 == 0 for IRR_F32 (1536 / 1920 / 2560 in the reference).
+ *   - re-entrant and thread-safe for distinct streams + workspaces.
+ *   - there is no CPU fallback: a device that is not sm_100 makes the bf16 tensor path return
+ *     IRR_ERR_UNSUPPORTED_DEVICE.
+ */
+#ifndef IRR_B200_H_
+#define IRR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define IRR_API
+#else
+#define IRR_API __attribute__((visibility("default")))
+#endif
+
+typedef int32_t irr_status;
+/* same object as cudaStream_t / CUstream */
+typedef struct CUstream_st* irr_stream_t;
+
+enum {
+  IRR_OK = 0,
+  IRR_ERR_INVALID_ARG = -1,        /* null pointer, negative size, k out of range ...      */
+  IRR_ERR_UNSUPPORTED_DTYPE = -2,
+  IRR_ERR_ALIGNMENT = -3,          /* pointer or D violates the alignment contract above   */
+  IRR_ERR_WORKSPACE_TOO_SMALL = -4,
+  IRR_ERR_K_TOO_LARGE = -5,        /* k > IRR_MAX_K                                         */
+  IRR_ERR_UNSUPPORTED_DEVICE = -6, /* not an sm_100 device / driver lacks tensor-map API   */
+  IRR_ERR_ROW_TOO_LONG = -7        /* D too large for the shared-memory staged loss kernels */
+};
+
+typedef enum { IRR_F32 = 0, IRR_BF16 = 1 } irr_dtype;
+
+/* largest k the register-resident top-k epilogues keep per query row */
+#define IRR_MAX_K 16
+
+/* which losses a pair/triplet call evaluates (bit mask) */
+enum { IRR_LOSS_COSINE_EMBEDDING = 1, IRR_LOSS_CONTRASTIVE = 2 };
+
+/* order of the four scalars of the triplet path, as logged separately by the reference
+ * (train/train_efficient_cos_con_ce_loss.py:396-399) */
+enum { IRR_L_COS_POS = 0, IRR_L_COS_NEG = 1, IRR_L_CON_POS = 2, IRR_L_CON_NEG = 3 };
+
+/* number of fp32 per-row statistics the loss forward saves for the backward kernel */
+#define IRR_ROW_STATS 8
+
+IRR_API int32_t     irr_version(void);
+IRR_API const char* irr_status_string(irr_status s);
+
+/* ------------------------------------------------------------------------------------------
+ * Cosine similarity + top-k (K1) — replaces, for ALL query rows at once,
+ *     sim = cos(fm_ims[idx].unsqueeze(0), fm_poss); vals, inds = torch.topk(sim, k)
+ *   train/train_efficient_cos_con_ce_loss.py:89,273,276,385,388
+ *   inference/inference.py:169,235,240      inference/training_analysis.ipynb:187,238
+ * with cos = CosineSimilarity(dim=1, eps): x1.x2 / (max(|x1|,eps) * max(|x2|,eps)).
+ *
+ * q [Q,D], g [N,D] of dtype `dt`; accumulate and emit fp32.
+ * g_inv_norm: optional device fp32[N] holding 1/max(|g_row|,eps) (cached by a gallery handle);
+ *             NULL = computed inside the call.
+ * out_val [Q,k] fp32 sorted descending, ties broken by LOWER gallery index;
+ * out_idx [Q,k] int64 = local row index + idx_offset (idx_offset = first row of this shard).
+ * Slots beyond N (k > N) hold (-inf, -1).   1 <= k <= IRR_MAX_K.
+ * The Q x N score matrix is never written to memory.
+ * ------------------------------------------------------------------------------------------ */
+IRR_API size_t irr_cosine_topk_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t k,
+                                               irr_dtype dt);
+IRR_API irr_status irr_cosine_topk(const void* q, const void* g, const float* g_inv_norm,
+                                   int64_t Q, int64_t N, int32_t D, int32_t k, irr_dtype dt,
+                                   float eps, int64_t idx_offset, float* out_val,
+                                   int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                                   irr_stream_t stream);
+
+/* Test / bring-up aid: the dense score matrix the bf16 tensor-core path ranks, out [Q,N] fp32
+ * (same kernel, epilogue writes scores instead of selecting).  Small N only. */
+IRR_API irr_status irr_cosine_scores_bf16(const void* q, const void* g, int64_t Q, int64_t N,
+                                          int32_t D, float eps, float* out_scores,
+                                          void* workspace, size_t workspace_bytes,
+                                          irr_stream_t stream);
+
+/* 1/max(|row|,eps) for every row of x [N,D] -> out fp32[N]; what a gallery handle caches. */
+IRR_API irr_status irr_row_inv_norms(const void* x, int64_t N, int32_t D, irr_dtype dt, float eps,
+                                     float* out, irr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Candidate merge (K3) — new in the sharded design: after one all-gather of
+ * every rank's [Q,k] (score, global index) lists, cand_* are [G,Q,k]; emits the global top-k
+ * [Q,k], descending, ties -> lower global index; entries with idx < 0 are padding.
+ * ------------------------------------------------------------------------------------------ */
+IRR_API irr_status irr_topk_merge(const float* cand_val, const int64_t* cand_idx, int32_t G,
+                                  int64_t Q, int32_t k, float* out_val, int64_t* out_idx,
+                                  irr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * top-1 / top-k hit accounting — replaces the per-row Python tests
+ *   class flavour    train/train_efficient_cos_con_ce_loss.py:279-281,390-392
+ *   instance flavour inference/inference.py:237,242
+ * idx [Q,k] int64 (output of irr_cosine_topk).
+ * class flavour:    q_label[Q], g_label[N] int64: hit if q_label[i] == g_label[idx[i][j]].
+ * instance flavour: q_label = g_label = NULL: hit if idx[i][j] == i + instance_offset.
+ * out_hits int64[2] = {#rows with a hit at j==0, #rows with a hit at any j<k}.
+ * ------------------------------------------------------------------------------------------ */
+IRR_API irr_status irr_topk_hits(const int64_t* idx, int64_t Q, int32_t k, const int64_t* q_label,
+                                 const int64_t* g_label, int64_t N, int64_t instance_offset,
+                                 int64_t* out_hits, irr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-wise cosine similarity — replaces cos(x1, x2) itself:
+ *   paired scores  train/train_efficient_cos_con_ce_loss.py:377,381   ipynb:232,234
+ *   one-vs-gallery train/train_efficient_cos_con_ce_loss.py:273       ipynb:238
+ * x2 [N,D]; x1 is [N,D] (x1_rows == N) or a single row broadcast against x2 (x1_rows == 1).
+ * out fp32[N].
+ * ------------------------------------------------------------------------------------------ */
+IRR_API irr_status irr_pair_cosine(const void* x1, int64_t x1_rows, const void* x2, int64_t N,
+                                   int32_t D, irr_dtype dt, float eps, float* out,
+                                   irr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Embedding losses (K2) — replaces
+ *   ContrastiveLoss.forward          utils/contrastive_loss.py:56-61
+ *   torch.nn.CosineEmbeddingLoss     train/train_efficient_cos_con_ce_loss.py:158,230-231,334-335
+ *   the four-loss composition        train/train_efficient_cos_con_ce_loss.py:230-237
+ *
+ * Triplet form: rows (q_i, p_i, n_i), i < B.  losses[4] (device fp32, order IRR_L_*):
+ *   cos_pos = red_i (1 - c(q,p))            cos_neg = red_i max(0, c(q,n) - margin_cos)
+ *   con_pos = red_i 0.5*|p-q|^2             con_neg = red_i 0.5*relu(margin_con - sqrt(|n-q|^2+1e-9))^2
+ *   c(a,b) = a.b / sqrt((|a|^2+1e-12)(|b|^2+1e-12)); red = mean (reduce_mean != 0) or sum.
+ * pair_cos: optional device fp32[2*B]: CosineSimilarity(dim=1, eps=pair_eps) of (q,p) then (q,n)
+ *   — the cos_sims / cos_unsims the reference logs (:377-382,402-403).
+ * row_stats: optional device fp32[B*IRR_ROW_STATS] saved for irr_triplet_loss_bwd.
+ * dq/dp/dn: optional (all three or none) gradients of sum_j grad_scale[j]*losses[j], written in
+ *   the same pass over the rows (fused forward+backward); dtype `dt`.
+ * n may be NULL ("pair form": only the *_POS terms... see irr_pair_loss_* below).
+ * ------------------------------------------------------------------------------------------ */
+IRR_API size_t irr_triplet_loss_workspace_bytes(int64_t B, int32_t D, irr_dtype dt);
+IRR_API irr_status irr_triplet_loss_fwd_bwd(const void* q, const void* p, const void* n, int64_t B,
+                                            int32_t D, irr_dtype dt, float margin_cos,
+                                            float margin_con, int32_t reduce_mean, float pair_eps,
+                                            float* losses, float* pair_cos, float* row_stats,
+                                            void* dq, void* dp, void* dn,
+                                            const float grad_scale[4], void* workspace,
+                                            size_t workspace_bytes, irr_stream_t stream);
+/* Backward from saved row statistics; grad_out = device fp32[4], the upstream gradients of the
+ * four scalars (read on the device: no host sync). */
+IRR_API irr_status irr_triplet_loss_bwd(const void* q, const void* p, const void* n,
+                                        const float* row_stats, const float* grad_out, int64_t B,
+                                        int32_t D, irr_dtype dt, float margin_cos, float margin_con,
+                                        int32_t reduce_mean, void* dq, void* dp, void* dn,
+                                        irr_stream_t stream);
+
+/* Pair form: ONE loss over rows (a_i, b_i) with a per-call or per-row label — the literal
+ * signatures ContrastiveLoss(margin)(fm1, fm2, label, mean) and
+ * CosineEmbeddingLoss(margin)(x1, x2, target).
+ *   kind = IRR_LOSS_CONTRASTIVE:      label y in [0,1] : 0.5*(y*d + (1-y)*relu(m - sqrt(d+1e-9))^2)
+ *   kind = IRR_LOSS_COSINE_EMBEDDING: target t in {1,-1}: t==1 ? 1-c : max(0, c-m)
+ * label: device fp32[label_count], label_count == 1 (broadcast) or B.
+ * loss: device fp32[1].  row_stats: optional fp32[B*IRR_ROW_STATS].
+ * da/db: optional (both or none) gradient of grad_scale*loss (fused forward+backward). */
+IRR_API size_t irr_pair_loss_workspace_bytes(int64_t B, int32_t D, irr_dtype dt);
+IRR_API irr_status irr_pair_loss_fwd_bwd(const void* a, const void* b, const float* label,
+                                         int64_t label_count, int64_t B, int32_t D, irr_dtype dt,
+                                         int32_t kind, float margin, int32_t reduce_mean,
+                                         float* loss, float* row_stats, void* da, void* db,
+                                         float grad_scale, void* workspace, size_t workspace_bytes,
+                                         irr_stream_t stream);
+IRR_API irr_status irr_pair_loss_bwd(const void* a, const void* b, const float* label,
+                                     int64_t label_count, const float* row_stats,
+                                     const float* grad_out, int64_t B, int32_t D, irr_dtype dt,
+                                     int32_t kind, float margin, int32_t reduce_mean, void* da,
+                                     void* db, irr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRR_B200_H_ */
