@@ -78,8 +78,10 @@ __device__ __forceinline__ RowOut triplet_row(const RowSums& s, float m_cos, flo
                                               const float (&w)[4]) {
   RowOut o;
   const float A = s.qq + kCosEmbEps, P = s.pp + kCosEmbEps, Nn = s.nn + kCosEmbEps;
-  const float rqp = rsqrtf(A * P), rqn = rsqrtf(A * Nn);
-  const float cqp = s.qp * rqp, cqn = s.qn * rqn;
+  // same operation order as ATen: cos = prod / sqrt(mag1 * mag2), IEEE sqrt and divide
+  const float dqp = sqrtf(A * P), dqn = sqrtf(A * Nn);
+  const float cqp = s.qp / dqp, cqn = s.qn / dqn;
+  const float rqp = 1.0f / dqp, rqn = 1.0f / dqn;
   o.l[IRR_L_COS_POS] = 1.0f - cqp;
   const float over = cqn - m_cos;
   o.l[IRR_L_COS_NEG] = fmaxf(over, 0.0f);
@@ -111,8 +113,9 @@ __device__ __forceinline__ RowOut pair_row(const RowSums& s, int kind, float y, 
     o.c.aqq = gcoef; o.c.aqp = -gcoef; o.c.app = gcoef;
   } else {
     const float A = s.qq + kCosEmbEps, P = s.pp + kCosEmbEps;
-    const float r = rsqrtf(A * P);
-    const float c = s.qp * r;
+    const float den = sqrtf(A * P);
+    const float c = s.qp / den;
+    const float r = 1.0f / den;
     float sign = 0.f;  // d loss / d c
     if (y == 1.0f) { o.l[0] = 1.0f - c; sign = -1.0f; }
     else if (y == -1.0f) { o.l[0] = fmaxf(c - margin, 0.0f); sign = (c - margin >= 0.0f) ? 1.0f : 0.0f; }
