@@ -72,12 +72,13 @@ def tied_gallery(N: int, D: int, Q: int, seed: int = 7, dtype=torch.float32):
     """Gallery with exact duplicate rows (score ties) to exercise the lower-index rule."""
     q, gal = iid_gallery(N, D, Q, seed)
     g = _gen(seed + 1)
-    src = torch.randint(0, N, (N // 4,), generator=g)
-    dst = torch.randint(0, N, (N // 4,), generator=g)
+    src = torch.randint(0, N, (max(N // 4, 1),), generator=g)
+    dst = torch.randint(0, N, (max(N // 4, 1),), generator=g)
     gal[dst] = gal[src]
-    # make the best match of every query a duplicated row
-    for i in range(Q):
-        a, b = int(src[i % len(src)]), int(dst[i % len(dst)])
-        gal[a] = q[i] * 0.5
-        gal[b] = q[i] * 0.5
+    # make the best match of every query an exactly duplicated row at two distinct positions
+    pairs = min(Q, N // 2)
+    where = torch.randperm(N, generator=g)[: 2 * pairs].view(pairs, 2)
+    for i in range(pairs):
+        gal[where[i, 0]] = q[i] * 0.5
+        gal[where[i, 1]] = q[i] * 0.5
     return q.to(dtype), gal.to(dtype)
