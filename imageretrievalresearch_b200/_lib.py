@@ -22,6 +22,7 @@ _i32, _i64, _f32, _sz, _vp = C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_vo
 SIGNATURES = {
     "irr_version": (_i32, []),
     "irr_status_string": (C.c_char_p, [_i32]),
+    "irr_profile_next_topk": (None, [_vp, _vp]),
     "irr_cosine_topk_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "irr_cosine_topk": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i64, _vp, _vp,
                                _vp, _sz, _vp]),

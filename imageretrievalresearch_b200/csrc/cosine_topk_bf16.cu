@@ -317,19 +317,17 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
                   int64_t Q, int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
                   float* scores, cudaStream_t st) {
   auto kern = cosine_topk_bf16_kernel<KMAX, WS>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-    attr_set = true;
-  }
+  IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
   const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
   // a gallery streamed by a single query tile is read exactly once: do not let it displace the
   // query tiles in L2; with several query tiles the gallery tiles are the L2-shared operand
   const uint64_t g_policy = p.m_tiles == 1 ? kPolicyEvictFirst : kPolicyEvictNormal;
+  if (!WS) profile_mark_start(st);
   kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(tq, tg, gin, qin, static_cast<int>(Q),
                                                 static_cast<int>(N), num_kb, k, p.m_tiles,
                                                 p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
                                                 scores, g_policy);
+  if (!WS) profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
 }

@@ -207,6 +207,7 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
     gin = gin_ws;
   }
   const int grid = p.m_tiles * p.n_chunks;
+  profile_mark_start(st);
   if (k <= 4) {
     auto kern = cosine_topk_f32_kernel<4>;
     IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -220,6 +221,7 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
                                             gin, static_cast<int>(Q), static_cast<int>(N), D, k,
                                             p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi);
   }
+  profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return merge_partials(pv, pi, p.n_chunks, Q, k, q, D, IRR_F32, eps, idx_offset, out_val, out_idx, st);
 }

@@ -33,6 +33,19 @@ int device_cc() {
 }
 
 namespace {
+thread_local cudaEvent_t g_prof_start = nullptr;
+thread_local cudaEvent_t g_prof_stop = nullptr;
+}  // namespace
+
+void profile_mark_start(cudaStream_t st) {
+  if (g_prof_start) cudaEventRecord(g_prof_start, st);
+}
+void profile_mark_stop(cudaStream_t st) {
+  if (g_prof_stop) cudaEventRecord(g_prof_stop, st);
+  g_prof_start = g_prof_stop = nullptr;
+}
+
+namespace {
 
 irr_status check_rows(const void* p, int32_t D, irr_dtype dt) {
   if (dt != IRR_F32 && dt != IRR_BF16) return IRR_ERR_UNSUPPORTED_DTYPE;
@@ -50,6 +63,11 @@ using namespace irr;
 extern "C" {
 
 int32_t irr_version(void) { return 100; }
+
+void irr_profile_next_topk(void* ev_start, void* ev_stop) {
+  g_prof_start = static_cast<cudaEvent_t>(ev_start);
+  g_prof_stop = static_cast<cudaEvent_t>(ev_stop);
+}
 
 const char* irr_status_string(irr_status s) {
   switch (s) {

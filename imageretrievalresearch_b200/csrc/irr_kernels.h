@@ -11,6 +11,10 @@
 
 namespace irr {
 
+// irr_cabi.cu: event pair armed by irr_profile_next_topk (thread-local, one-shot)
+void profile_mark_start(cudaStream_t st);
+void profile_mark_stop(cudaStream_t st);
+
 // row_norms.cu
 irr_status row_inv_norms(const void* x, int64_t N, int32_t D, irr_dtype dt, float eps, float* out,
                          cudaStream_t st);

@@ -102,6 +102,12 @@ IRR_API irr_status irr_cosine_scores_bf16(const void* q, const void* g, int64_t 
                                           void* workspace, size_t workspace_bytes,
                                           irr_stream_t stream);
 
+/* Measurement aid (bench.py's roofline leg): arm a pair of caller-created cudaEvent_t; the NEXT
+ * irr_cosine_topk call made by this host thread records them on its stream immediately before and
+ * after the dominant top-k kernel (excluding the norm pre-pass and the partial-list merge), then
+ * disarms.  Pass NULLs to disarm. */
+IRR_API void irr_profile_next_topk(void* ev_start, void* ev_stop);
+
 /* 1/max(|row|,eps) for every row of x [N,D] -> out fp32[N]; what a gallery handle caches. */
 IRR_API irr_status irr_row_inv_norms(const void* x, int64_t N, int32_t D, irr_dtype dt, float eps,
                                      float* out, irr_stream_t stream);

@@ -1,0 +1,419 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the oracle and the
+golden vectors generated from the reference.  Tolerances are north_star's:
+  fp32 mode: top-k scores within 1e-5 relative;  bf16 mode: within 2e-2 absolute;
+  indices identical except where the oracle's score gap is below that tolerance;
+  top1/top3 identical; losses within 1e-5 relative, gradients within 1e-4 relative.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import imageretrievalresearch_b200 as irr
+from imageretrievalresearch_b200 import _lib, _ops
+from oracle import reference_path as ref
+from oracle import synthetic
+
+pytestmark = pytest.mark.gpu
+
+FP32_REL = 1e-5
+BF16_ABS = 2e-2
+LOSS_REL = 1e-5
+GRAD_REL = 1e-4
+MARGINS = (0.2, 0.3, 0.5)
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.asarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def check_topk(res, q, g, k, tol, relative):
+    _, _, s = ref.cos_topk_stable(q.cpu(), g.cpu(), min(k, g.shape[0]))
+    m = ref.topk_matches(res.values[:, : min(k, g.shape[0])], res.indices[:, : min(k, g.shape[0])],
+                         s, min(k, g.shape[0]), tol, relative)
+    assert m["val_err"] <= tol, m
+    assert m["bad_idx"] == 0, m
+    return m
+
+
+# -------------------------------------------------------------------------------------------------
+# golden vectors (outputs of the reference itself)
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["unit", "scaled"])
+@pytest.mark.parametrize("margin", MARGINS)
+def test_golden_losses_and_grads(golden_losses, tag, margin):
+    g = golden_losses
+    q, p, n = T(g[f"{tag}_q"]), T(g[f"{tag}_p"]), T(g[f"{tag}_n"])
+    key = f"{tag}_m{margin}"
+    want = T(g[key + "_losses"])
+    out = irr.triplet_losses_fwd_bwd(q, p, n, margin, pair_scores=True)
+    assert ((out.losses - want).abs() <= LOSS_REL * want.abs() + 1e-9).all(), (out.losses, want)
+    for got, name in ((out.grad_qry, "_dq"), (out.grad_pos, "_dp"), (out.grad_neg, "_dn")):
+        assert rel(got, T(g[key + name])) < GRAD_REL, name
+    assert (out.pair_cos[0] - T(g[f"{tag}_cos_sims"])).abs().max() < 1e-6
+    assert (out.pair_cos[1] - T(g[f"{tag}_cos_unsims"])).abs().max() < 1e-6
+    # autograd-integrated form, loss = loss_cos + loss_con as in training_step
+    qa, pa, na = [t.clone().requires_grad_(True) for t in (q, p, n)]
+    tl = irr.triplet_losses(qa, pa, na, margin)
+    (tl.loss_cos + tl.loss_con).backward()
+    for got, name in ((qa.grad, "_dq"), (pa.grad, "_dp"), (na.grad, "_dn")):
+        assert rel(got, T(g[key + name])) < GRAD_REL, name
+    # drop-in modules, reference call signatures (labels as [1] tensors and python floats)
+    con, cel = irr.ContrastiveLoss(margin), irr.CosineEmbeddingLoss(margin)
+    got = torch.stack([cel(q, p, torch.tensor(1.).unsqueeze(0).cuda()),
+                       cel(q, n, torch.tensor(-1.).unsqueeze(0).cuda()),
+                       con(q, p, torch.tensor(1.).unsqueeze(0).cuda()), con(q, n, 0.)])
+    assert ((got - want).abs() <= LOSS_REL * want.abs() + 1e-9).all()
+    sums = T(g[key + "_con_sum"])
+    got_sum = torch.stack([con(q, p, 1., mean=False), con(q, n, 0., mean=False)])
+    assert ((got_sum - sums).abs() <= LOSS_REL * sums.abs() + 1e-9).all()
+    assert got[0].dim() == 0 and got[0].dtype == torch.float32
+
+
+def test_golden_retrieval(golden_retrieval):
+    g = golden_retrieval
+    q, gal = T(g["planted_q"]), T(g["planted_g"])
+    res = irr.cosine_topk(q, gal, 3)
+    assert torch.equal(res.indices, T(g["planted_inds"]))
+    assert ((res.values - T(g["planted_vals"])).abs() <= FP32_REL * T(g["planted_vals"]).abs()).all()
+    hits = irr.topk_hits(res.indices, T(g["planted_clss_q"]), T(g["planted_clss_g"]))
+    assert hits.tolist() == [int(g["planted_top1"]), int(g["planted_top3"])]
+    # bf16 mode on the same vectors: planted gaps >> 2e-2
+    rb = irr.cosine_topk(q.bfloat16(), gal.bfloat16(), 3)
+    assert torch.equal(rb.indices, T(g["planted_inds"]))
+    assert (rb.values - T(g["planted_vals"])).abs().max() < BF16_ABS
+    # training-step flavour (gallery = batch of positives)
+    bq, bp, cl = T(g["batch_q"]), T(g["batch_p"]), T(g["batch_clss"])
+    top1, top3, r = irr.top1_top3(bq, bp, cl, cl)
+    assert abs(top1.item() * 16 - int(g["batch_top1"])) < 1e-4
+    assert abs(top3.item() * 16 - int(g["batch_top3"])) < 1e-4
+    assert ((r.values - T(g["batch_vals"])).abs() <= FP32_REL * T(g["batch_vals"]).abs()).all()
+    # k = 10 values on an iid gallery
+    r10 = irr.cosine_topk(T(g["iid_q"]), T(g["iid_g"]), 10)
+    assert ((r10.values - T(g["iid_vals10"])).abs() <= FP32_REL * T(g["iid_vals10"]).abs() + 1e-7).all()
+
+
+# -------------------------------------------------------------------------------------------------
+# BASELINE.json configs[1]: 10k x 1536 fp32, Q=64, k=3 — exactness vs torch
+# -------------------------------------------------------------------------------------------------
+def test_config_fp32_10k_exactness():
+    q, gal, pos = synthetic.planted_gallery(10_000, 1536, 64, 3, seed=1)
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), 3)
+    m = check_topk(res, q, gal, 3, FP32_REL, relative=True)
+    assert torch.equal(res.indices.cpu(), pos)
+    # and against the literal per-query reference loop
+    lv, li = ref.cos_topk_loop(q, gal, 3)
+    assert torch.equal(res.indices.cpu(), li)
+    assert ((res.values.cpu() - lv).abs() <= FP32_REL * lv.abs()).all()
+    # iid queries: near-ties possible, tolerance-aware index check
+    q2, gal2 = synthetic.iid_gallery(10_000, 1536, 64, seed=5)
+    check_topk(irr.cosine_topk(q2.cuda(), gal2.cuda(), 3), q2, gal2, 3, FP32_REL, relative=True)
+
+
+# -------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2]: fused losses fwd/bwd on 4096 x 1536 triplets, margins 0.2/0.3/0.5
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scaled", [False, True])
+def test_config_losses_4096(scaled):
+    q, p, n = synthetic.triplets(4096, 1536, seed=2, scaled=scaled)
+    qc, pc, nc = q.cuda(), p.cuda(), n.cuda()
+    w = (1.0, 0.7, 1.3, 2.0)
+    for margin in MARGINS:
+        want, dq, dp, dn = ref.four_losses_and_grads(q, p, n, margin, weights=w)
+        out = irr.triplet_losses_fwd_bwd(qc, pc, nc, margin, grad_scale=w)
+        got = out.losses.cpu()
+        assert ((got - want).abs() <= LOSS_REL * want.abs() + 1e-9).all(), (margin, got, want)
+        assert rel(out.grad_qry.cpu(), dq) < GRAD_REL
+        assert rel(out.grad_pos.cpu(), dp) < GRAD_REL
+        assert rel(out.grad_neg.cpu(), dn) < GRAD_REL
+        # autograd path with unequal upstream gradients
+        qa, pa, na = [t.clone().requires_grad_(True) for t in (qc, pc, nc)]
+        tl = irr.triplet_losses(qa, pa, na, margin)
+        (w[0] * tl.cos_pos + w[1] * tl.cos_neg + w[2] * tl.con_pos + w[3] * tl.con_neg).backward()
+        assert rel(qa.grad.cpu(), dq) < GRAD_REL and rel(na.grad.cpu(), dn) < GRAD_REL
+    # determinism: same inputs, same bits
+    a = irr.triplet_losses_fwd_bwd(qc, pc, nc, 0.3)
+    b = irr.triplet_losses_fwd_bwd(qc, pc, nc, 0.3)
+    assert torch.equal(a.losses, b.losses) and torch.equal(a.grad_neg, b.grad_neg)
+
+
+def test_losses_bf16_inputs_and_shapes():
+    for B, D in [(333, 1920), (7, 2560), (1, 8), (65, 1536)]:
+        q, p, n = synthetic.triplets(B, D, seed=B)
+        qb, pb, nb = [t.cuda().bfloat16() for t in (q, p, n)]
+        want, dq, dp, dn = ref.four_losses_and_grads(qb.float().cpu(), pb.float().cpu(),
+                                                     nb.float().cpu(), 0.3)
+        out = irr.triplet_losses_fwd_bwd(qb, pb, nb, 0.3)
+        assert ((out.losses.cpu() - want).abs() <= LOSS_REL * want.abs() + 1e-8).all()
+        assert out.grad_qry.dtype == torch.bfloat16
+        # gradients are rounded to bf16 on store: 2^-8 relative per element
+        assert rel(out.grad_qry.float().cpu(), dq) < 4e-3
+        assert rel(out.grad_neg.float().cpu(), dn) < 4e-3
+
+
+def test_losses_sum_reduction_and_per_row_labels():
+    q, p, n = synthetic.triplets(50, 64, seed=3)
+    y = (torch.arange(50) % 2).float()
+    t = 1 - 2 * y
+    qc, nc = q.cuda().requires_grad_(True), n.cuda().requires_grad_(True)
+    got = irr.ContrastiveLoss(0.5)(qc, nc, y.cuda(), mean=False)
+    got.backward()
+    qr, nr = q.clone().requires_grad_(True), n.clone().requires_grad_(True)
+    want = ref.contrastive_loss(qr, nr, y, 0.5, mean=False)
+    want.backward()
+    assert abs(got.item() - want.item()) <= LOSS_REL * abs(want.item())
+    assert rel(qc.grad.cpu(), qr.grad) < GRAD_REL and rel(nc.grad.cpu(), nr.grad) < GRAD_REL
+    got = irr.CosineEmbeddingLoss(0.2, reduction="sum")(q.cuda(), n.cuda(), t.cuda())
+    want = torch.nn.CosineEmbeddingLoss(0.2, reduction="sum")(q, n, t)
+    assert abs(got.item() - want.item()) <= LOSS_REL * abs(want.item())
+
+
+def test_fp16_autocast_embeddings_are_widened():
+    q, p, n = synthetic.triplets(32, 128, seed=4)
+    qh = q.cuda().half()
+    want = ref.four_losses(qh.float().cpu(), p, n, 0.3)
+    tl = irr.triplet_losses(qh, p.cuda(), n.cuda(), 0.3)
+    got = torch.stack([tl.cos_pos, tl.cos_neg, tl.con_pos, tl.con_neg]).cpu()
+    assert ((got - want).abs() <= LOSS_REL * want.abs() + 1e-8).all()
+
+
+# -------------------------------------------------------------------------------------------------
+# edge cases: ragged shapes, ties, zero rows, short shards, k range, errors
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Q,N,D,k", [(1, 1, 8, 1), (1, 257, 200, 3), (5, 100, 72, 16), (129, 255, 64, 1),
+                                     (200, 777, 1920, 10), (64, 4097, 2560, 3), (3, 513, 8, 4)])
+def test_ragged_shapes(dtype, Q, N, D, k):
+    k = min(k, N)
+    q, gal = synthetic.iid_gallery(N, D, Q, seed=N + Q)
+    q, gal = q.to(dtype), gal.to(dtype)
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), k)
+    tol, relative = (FP32_REL, True) if dtype == torch.float32 else (1e-4, False)
+    check_topk(res, q, gal, k, tol, relative)
+    assert res.values.dtype == torch.float32 and res.indices.dtype == torch.int64
+    assert (res.values[:, :-1] >= res.values[:, 1:]).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ties_resolve_to_lower_index(dtype):
+    q, gal = synthetic.tied_gallery(3000, 64, 40, seed=7, dtype=dtype)
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), 4)
+    _, want_i, s = ref.cos_topk_stable(q, gal, 4)
+    # duplicated rows give bit-identical scores on the device, so the order is fully determined
+    dup = s.gather(1, want_i)
+    exact_tie = dup[:, 0] == dup[:, 1]
+    assert exact_tie.any()
+    assert torch.equal(res.indices.cpu()[:, :2], want_i[:, :2])
+    assert (res.indices[:, 0] < res.indices[:, 1]).all()
+    assert (res.values[:, 0] == res.values[:, 1]).all()
+
+
+def test_zero_norm_rows_and_eps():
+    q, gal = synthetic.iid_gallery(500, 64, 8, seed=11)
+    gal[17] = 0
+    q[3] = 0
+    gal[40] = 1e-9 * gal[40]          # |g| < eps: clamped, not normalised
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), 3)
+    check_topk(res, q, gal, 3, FP32_REL, relative=True)
+    assert (res.values[3] == 0).all() and res.indices[3].tolist() == [0, 1, 2]  # all-zero scores: lowest indices
+    cs = irr.CosineSimilarity(dim=1, eps=1e-6)
+    want = torch.nn.CosineSimilarity(dim=1, eps=1e-6)(q[:1], gal)
+    assert (cs(q[:1].cuda(), gal.cuda()).cpu() - want).abs().max() < 1e-6
+    want = torch.nn.CosineSimilarity(dim=1, eps=1e-6)(gal[:8], q)
+    assert (cs(gal[:8].cuda(), q.cuda()).cpu() - want).abs().max() < 1e-6
+
+
+def test_short_shard_and_errors():
+    q, gal = synthetic.iid_gallery(2, 64, 4, seed=2)
+    with pytest.raises(RuntimeError, match="out of range"):
+        irr.cosine_topk(q.cuda(), gal.cuda(), 3)
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), 3, allow_short=True, idx_offset=100)
+    assert (res.indices[:, 2] == -1).all() and torch.isinf(res.values[:, 2]).all()
+    assert set(res.indices[0, :2].tolist()) == {100, 101}
+    with pytest.raises(ValueError):
+        irr.cosine_topk(q.cuda(), gal.cuda(), irr.IRR_MAX_K + 1)
+    with pytest.raises(irr.IrrError) as e:   # D=12 bf16 rows are not 16-byte multiples
+        irr.cosine_topk(torch.randn(2, 12).cuda().bfloat16(), torch.randn(9, 12).cuda().bfloat16(), 1)
+    assert e.value.status == -3
+    with pytest.raises(RuntimeError, match="widths differ"):
+        irr.cosine_topk(torch.randn(2, 16).cuda(), torch.randn(9, 32).cuda(), 1)
+
+
+def test_hits_flavours():
+    torch.manual_seed(0)
+    idx = torch.randint(0, 2000, (500, 3))
+    ql, gl = torch.randint(0, 8, (500,)), torch.randint(0, 8, (2000,))
+    assert irr.topk_hits(idx.cuda(), ql.cuda(), gl.cuda()).tolist() == list(ref.hits_from_indices(idx, ql, gl))
+    idx[::7, 1] = torch.arange(0, 500, 7)
+    assert irr.topk_hits(idx.cuda()).tolist() == list(ref.hits_from_indices(idx, None, None))
+    assert irr.topk_hits(idx.cuda() + 50, instance_offset=50).tolist() == \
+        list(ref.hits_from_indices(idx + 50, None, None, 50))
+
+
+@pytest.mark.parametrize("G,Q,k", [(8, 100, 3), (2, 7, 10), (4, 33, 1), (8, 64, 16), (1, 5, 3)])
+def test_merge_kernel_vs_oracle(G, Q, k):
+    torch.manual_seed(G * 100 + k)
+    vals = torch.randn(G, Q, k).sort(dim=2, descending=True).values
+    idx = torch.stack([torch.randperm(1000)[:k].sort().values + g * 1000
+                       for g in range(G) for _ in range(Q)]).view(G, Q, k)
+    if G > 1:
+        vals[0, :, 0] = vals[1, :, 0]         # cross-shard ties
+        idx[G - 1, ::3, k - 1] = -1           # padding from a short shard
+        vals[G - 1, ::3, k - 1] = -float("inf")
+    v, i = _ops.topk_merge(vals.cuda(), idx.cuda())
+    wv, wi = ref.merge_candidates(vals, idx, k)
+    assert torch.equal(i.cpu(), wi) and torch.equal(v.cpu(), wv)
+
+
+# -------------------------------------------------------------------------------------------------
+# bf16 tensor-core path: dense scores and top-k at medium size
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Q,N,D", [(128, 512, 1536), (64, 1000, 1536), (300, 3000, 1920), (1, 257, 200)])
+def test_bf16_dense_scores(Q, N, D):
+    q, gal = synthetic.iid_gallery(N, D, Q, seed=Q + N, dtype=torch.bfloat16)
+    got = _ops.cosine_scores_bf16(q.cuda(), gal.cuda(), 1e-6)
+    want = ref.cos_scores(q, gal)
+    assert (got.double().cpu() - want).abs().max() < 1e-5   # far inside the 2e-2 bf16 bar
+
+
+def test_bf16_planted_100k():
+    q, gal, pos = synthetic.planted_gallery(100_000, 1536, 300, 3, seed=3, dtype=torch.bfloat16)
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), 3)
+    assert torch.equal(res.indices.cpu(), pos)
+    check_topk(res, q, gal, 3, BF16_ABS, relative=False)
+    # bf16 result vs the fp32 reference on the un-rounded data stays within the bf16 bar too
+    q32, gal32, _ = synthetic.planted_gallery(100_000, 1536, 300, 3, seed=3)
+    lv = ref.cos_scores(q32, gal32).gather(1, pos)
+    assert (res.values.cpu().double() - lv).abs().max() < BF16_ABS
+    # cached-norm gallery handle gives the same bits
+    gal_h = irr.Gallery(gal.cuda())
+    r2 = gal_h.search(q.cuda(), 3)
+    assert torch.equal(r2.indices, res.indices) and torch.equal(r2.values, res.values)
+
+
+def test_k10_bf16_d2560():
+    q, gal, pos = synthetic.planted_gallery(50_000, 2560, 130, 10, seed=4, dtype=torch.bfloat16)
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), 10)
+    check_topk(res, q, gal, 10, BF16_ABS, relative=False)
+    assert torch.equal(res.indices.cpu().sort(dim=1).values, pos.sort(dim=1).values)
+
+
+# -------------------------------------------------------------------------------------------------
+# full-size headline config: 1M x 1536 bf16, Q = 1 / 64 / 4096 — size-independent properties
+# -------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gallery_1m():
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    g = torch.randn(1_000_000, 1536, device="cuda", dtype=torch.bfloat16, generator=gen)
+    return g
+
+
+@pytest.mark.parametrize("Q", [1, 64, 4096])
+def test_headline_1m_planted(gallery_1m, Q):
+    g = gallery_1m
+    N, D = g.shape
+    gen = torch.Generator(device="cuda").manual_seed(100 + Q)
+    base = torch.randn(Q, D, device="cuda", generator=gen)
+    pos = torch.randperm(N, device="cuda", generator=gen)[: Q * 3].view(Q, 3)
+    saved = g[pos.flatten()].clone()
+    try:
+        for j, sig in enumerate((0.010, 0.018, 0.026)):
+            g[pos[:, j]] = (base + sig * D ** 0.5 * torch.randn(Q, D, device="cuda", generator=gen)).bfloat16()
+        q = (3.7 * base).bfloat16()
+        res = irr.cosine_topk(q, g, 3)
+        assert torch.equal(res.indices, pos)                      # planted rows, in rank order
+        # values against torch's own cosine_similarity on the selected rows (fp32 on bf16 data)
+        want = torch.nn.functional.cosine_similarity(q.float().unsqueeze(1), g[res.indices].float(),
+                                                     dim=2, eps=1e-6)
+        assert (res.values - want).abs().max() < 1e-5
+        # idempotence / determinism
+        r2 = irr.cosine_topk(q, g, 3)
+        assert torch.equal(r2.indices, res.indices) and torch.equal(r2.values, res.values)
+        # row-sharded emulation on one device: G shards with offsets + merge kernel == unsharded
+        for G in (2, 8):
+            cv, ci = [], []
+            for r in range(G):
+                lo, hi = irr.shard_bounds(N, G, r)
+                part = irr.cosine_topk(q, g[lo:hi], 3, idx_offset=lo)
+                cv.append(part.values)
+                ci.append(part.indices)
+            mv, mi = _ops.topk_merge(torch.stack(cv), torch.stack(ci))
+            assert torch.equal(mi, res.indices) and torch.equal(mv, res.values)
+        # a random sample of the queries against a chunked torch fp32 scan of the whole gallery
+        sel = torch.arange(Q, device="cuda")[: min(Q, 16)]
+        qs = torch.nn.functional.normalize(q[sel].float(), dim=1)
+        best_v = torch.full((len(sel), 3), -2.0, device="cuda")
+        best_i = torch.zeros((len(sel), 3), dtype=torch.int64, device="cuda")
+        for lo in range(0, N, 125_000):
+            blk = torch.nn.functional.normalize(g[lo:lo + 125_000].float(), dim=1)
+            v, i = torch.topk(qs @ blk.T, 3, dim=1)
+            allv, alli = torch.cat([best_v, v], 1), torch.cat([best_i, i + lo], 1)
+            o = torch.argsort(allv, dim=1, descending=True, stable=True)[:, :3]
+            best_v, best_i = allv.gather(1, o), alli.gather(1, o)
+        assert torch.equal(best_i, res.indices[sel])
+        assert (best_v - res.values[sel]).abs().max() < BF16_ABS
+    finally:
+        g[pos.flatten()] = saved
+
+
+# -------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0]: CNN embeddings (random-init efficientnet_b3, 1536-d pooled features)
+# -------------------------------------------------------------------------------------------------
+def test_config_backbone_embeddings_end_to_end():
+    tv = pytest.importorskip("torchvision")
+    torch.manual_seed(0)
+    net = tv.models.efficientnet_b3(weights=None).features.cuda().eval()
+    B = 64
+    with torch.no_grad():
+        fms = []
+        for _ in range(3):
+            x = torch.rand(B, 3, 224, 224, device="cuda")
+            fm = net(x)                                             # [B,1536,7,7]
+            pool = torch.nn.AvgPool2d((fm.shape[2], fm.shape[3]))   # get_fm, reference :103-122
+            fms.append(pool(fm).reshape(-1, fm.shape[1]))
+    q, p, n = fms
+    assert q.shape == (B, 1536)
+    clss = (torch.arange(B) % 8).cuda()
+    margin = 0.3
+    want = ref.four_losses(q.cpu(), p.cpu(), n.cpu(), margin)
+    tl = irr.triplet_losses(q, p, n, margin, pair_scores=True)
+    got = torch.stack([tl.cos_pos, tl.cos_neg, tl.con_pos, tl.con_neg]).cpu()
+    assert ((got - want).abs() <= LOSS_REL * want.abs() + 1e-8).all(), (got, want)
+    sims, unsims = ref.paired_scores(q.cpu(), p.cpu(), n.cpu())
+    assert (tl.pair_cos_pos.cpu() - sims).abs().max() < 1e-6
+    assert (tl.pair_cos_neg.cpu() - unsims).abs().max() < 1e-6
+    top1, top3, res = irr.top1_top3(q, p, clss, clss)
+    # random-init CNN features are nearly collinear (cos > 0.99): gaps are tiny, so compare the
+    # accounting on the kernel's own indices and the indices tolerance-aware
+    check_topk(res, q.cpu(), p.cpu(), 3, FP32_REL, relative=True)
+    w1, w3 = ref.hits_from_indices(res.indices, clss.cpu(), clss.cpu())
+    assert abs(top1.item() * B - w1) < 1e-3 and abs(top3.item() * B - w3) < 1e-3
+
+
+# -------------------------------------------------------------------------------------------------
+# the raw C ABI with hand-built arguments (no python wrapper logic in between)
+# -------------------------------------------------------------------------------------------------
+def test_raw_cabi_call():
+    lib = _lib.load()
+    q, gal, pos = synthetic.planted_gallery(5000, 256, 10, 3, seed=8, dtype=torch.bfloat16)
+    qd, gd = q.cuda(), gal.cuda()
+    vals = torch.empty(10, 3, device="cuda")
+    idx = torch.empty(10, 3, dtype=torch.int64, device="cuda")
+    need = lib.irr_cosine_topk_workspace_bytes(10, 5000, 256, 3, _lib.IRR_BF16)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    st = lib.irr_cosine_topk(qd.data_ptr(), gd.data_ptr(), None, 10, 5000, 256, 3, _lib.IRR_BF16,
+                             1e-6, 7, vals.data_ptr(), idx.data_ptr(), ws.data_ptr(), need,
+                             torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    torch.cuda.synchronize()
+    assert torch.equal(idx.cpu(), pos + 7)
+    small = torch.empty(16, dtype=torch.uint8, device="cuda")
+    st = lib.irr_cosine_topk(qd.data_ptr(), gd.data_ptr(), None, 10, 5000, 256, 3, _lib.IRR_BF16,
+                             1e-6, 0, vals.data_ptr(), idx.data_ptr(), small.data_ptr(), 16, None)
+    assert st == -4
