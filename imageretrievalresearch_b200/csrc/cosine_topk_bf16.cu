@@ -4,7 +4,7 @@
 // loops (train/train_efficient_cos_con_ce_loss.py:270-281,374-392;
 // inference/training_analysis.ipynb:231-251) for all query rows in one launch.
 //
-// Layout / roles (one persistent CTA per SM, 256 threads):
+// Layout / roles (one persistent CTA per SM, 384 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles of Q (128 x 64) and G (256 x 64),
 //               128-byte swizzle, into a 4-stage shared-memory ring (48 KB / stage)
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256, K=16) x4 per stage,
@@ -13,6 +13,8 @@
 //   warps 4-7   epilogue: tcgen05.ld the accumulator (thread = query row, 32 columns at a time),
 //               scale by 1/max(|g|,eps), keep a running sorted top-k per row in registers.
 //               The Q x N scores never leave the SM.
+//   warps 8-11  (single-query-tile searches) gallery-norm warps: L2-normalisation fused into the
+//               load — they square-sum each gallery row from the shared-memory stages the MMA reads
 // Work unit = (query tile of 128 rows, chunk of consecutive 256-row gallery tiles); units are
 // numbered query-tile-fastest so that CTAs running at the same time share gallery tiles in L2.
 // Every unit writes a [128, k] partial list; topk_merge.cu folds the partials, applies
@@ -36,14 +38,16 @@ constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
+constexpr int NORM_WARP0 = 8;   // warps 8-11: gallery-norm warps of the fused-norm variant
+constexpr int NORM_THREADS = 128;
 
 // dynamic shared memory carve-up (base aligned to 1024 B for the 128-byte swizzle)
 constexpr int SMEM_TILES = STAGES * STAGE_BYTES;                 // 196608
 constexpr int SMEM_GN = ACC_STAGES * BLOCK_N * 4;                // inverse gallery norms per tile
-constexpr int SMEM_BARS = (2 * STAGES + 2 * ACC_STAGES) * 8;
+constexpr int SMEM_BARS = (2 * STAGES + 3 * ACC_STAGES) * 8;
 constexpr int SMEM_TOTAL = SMEM_TILES + SMEM_GN + SMEM_BARS + 16;
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;                    // slack for manual alignment
 
@@ -81,7 +85,11 @@ Plan make_plan(int64_t Q, int64_t N) {
   return p;
 }
 
-template <int KMAX, bool WRITE_SCORES>
+// FUSE_NORM (single query tile: every gallery tile is consumed by exactly one CTA): four extra
+// warps square-sum the gallery rows out of the SAME shared-memory stages the MMA reads, so the
+// gallery crosses HBM once per search and no inverse-norm pre-pass exists.  With several query
+// tiles a gallery tile is consumed by many CTAs and the norms come from g_inv_norm instead.
+template <int KMAX, bool WRITE_SCORES, bool FUSE_NORM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         const __grid_constant__ CUtensorMap tmap_g,
@@ -89,7 +97,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         int Q, int N, int num_kb, int k, int m_tiles, int n_tiles,
                         int tiles_per_chunk, int n_chunks, float* __restrict__ part_val,
                         int32_t* __restrict__ part_idx, float* __restrict__ scores_out,
-                        uint64_t g_policy) {
+                        uint64_t g_policy, float eps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -99,6 +107,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC_STAGES + s); };
+  auto gnfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 * ACC_STAGES + s); };
   const uint32_t tmem_slot = bars + SMEM_BARS;
   float* gn_smem = reinterpret_cast<float*>(smem_gen + SMEM_TILES);
   volatile uint32_t* tmem_slot_gen =
@@ -114,11 +123,14 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      // a stage is free once its MMAs retired (tcgen05.commit) and, when the norms are fused,
+      // once each of the four norm warps has read it
+      mbar_init(empty_bar(s), FUSE_NORM ? 1 + NORM_THREADS / 32 : 1);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), EPI_THREADS / 32);
+      mbar_init(gnfull_bar(s), NORM_THREADS / 32);
     }
     fence_mbar_init();
   }
@@ -190,7 +202,60 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else if (FUSE_NORM && warp >= NORM_WARP0) {
+    // ===================== gallery-norm warps (fused-norm variant) =====================
+    // thread nt owns gallery rows nt and nt+128 of the tile.  A row is 128 bytes per stage; the
+    // TMA swizzle only permutes the eight 16-byte chunks inside that row, which a sum of squares
+    // does not care about.  Chunk order is rotated by the thread index so that the eight lanes
+    // of a quarter-warp hit eight different bank groups (conflict-free LDS.128).
+    const int nt = threadIdx.x - NORM_WARP0 * 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int chunk = u / m_tiles;
+      const int t0 = chunk * tiles_per_chunk;
+      const int t1 = min(t0 + tiles_per_chunk, n_tiles);
+      for (int t = t0; t < t1; ++t, ++it) {
+        float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, 600 + stage);
+          const uint8_t* b = smem_gen + stage * STAGE_BYTES + A_STAGE_BYTES;
+          const uint4* r0 = reinterpret_cast<const uint4*>(b + nt * 128);
+          const uint4* r1 = reinterpret_cast<const uint4*>(b + (nt + NORM_THREADS) * 128);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const uint4 u0 = r0[(j + nt) & 7], u1 = r0[(j + 1 + nt) & 7];
+            const uint4 w0 = r1[(j + nt) & 7], w1 = r1[(j + 1 + nt) & 7];
+            const uint32_t x0[4] = {u0.x, u0.y, u0.z, u0.w}, x1[4] = {u1.x, u1.y, u1.z, u1.w};
+            const uint32_t y0[4] = {w0.x, w0.y, w0.z, w0.w}, y1[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = bf16lo(x0[e]), c = bf16hi(x0[e]);
+              s0a = fmaf(a, a, s0a); s0a = fmaf(c, c, s0a);
+              a = bf16lo(x1[e]); c = bf16hi(x1[e]);
+              s0b = fmaf(a, a, s0b); s0b = fmaf(c, c, s0b);
+              a = bf16lo(y0[e]); c = bf16hi(y0[e]);
+              s1a = fmaf(a, a, s1a); s1a = fmaf(c, c, s1a);
+              a = bf16lo(y1[e]); c = bf16hi(y1[e]);
+              s1b = fmaf(a, a, s1b); s1b = fmaf(c, c, s1b);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        // the epilogue must be done with the norms it read two tiles ago from this buffer
+        mbar_wait(tempty_bar(as), aphase ^ 1u, 700 + as);
+        float* gn = gn_smem + as * BLOCK_N;
+        gn[nt] = 1.0f / fmaxf(sqrtf(s0a + s0b), eps);
+        gn[nt + NORM_THREADS] = 1.0f / fmaxf(sqrtf(s1a + s1b), eps);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gnfull_bar(as));
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < NORM_WARP0) {
     // ===================== epilogue: scale + running top-k =====================
     const int ew = warp - EPI_WARP0;          // == warp % 4: TMEM lane quarter this warp may read
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
@@ -210,12 +275,14 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         const int n0 = t * BLOCK_N;
         float* gn = gn_smem + as * BLOCK_N;
-        {
+        if (FUSE_NORM) {
+          mbar_wait(gnfull_bar(as), aphase, 800 + as);   // norm warps published this tile's norms
+        } else {
           const int c0 = n0 + et, c1 = n0 + et + EPI_THREADS;
           gn[et] = c0 < N ? __ldg(g_inv_norm + c0) : 0.0f;
           gn[et + EPI_THREADS] = c1 < N ? __ldg(g_inv_norm + c1) : 0.0f;
+          named_bar_sync(1, EPI_THREADS);
         }
-        named_bar_sync(1, EPI_THREADS);
         mbar_wait(tfull_bar(as), aphase, 400 + as);
         tcgen05_fence_after();
         const int n_valid = min(BLOCK_N, N - n0);
@@ -312,11 +379,11 @@ bool encode_bf16_rows(CUtensorMap* m, const void* base, int64_t rows, int64_t co
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int KMAX, bool WS>
+template <int KMAX, bool WS, bool FN>
 irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, const float* qin,
                   int64_t Q, int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
-                  float* scores, cudaStream_t st) {
-  auto kern = cosine_topk_bf16_kernel<KMAX, WS>;
+                  float* scores, float eps, cudaStream_t st) {
+  auto kern = cosine_topk_bf16_kernel<KMAX, WS, FN>;
   IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
   const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
   // a gallery streamed by a single query tile is read exactly once: do not let it displace the
@@ -326,7 +393,7 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
   kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(tq, tg, gin, qin, static_cast<int>(Q),
                                                 static_cast<int>(N), num_kb, k, p.m_tiles,
                                                 p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
-                                                scores, g_policy);
+                                                scores, g_policy, eps);
   if (!WS) profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -357,8 +424,11 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   w += align_up(parts * 4, 256);
   int32_t* pi = reinterpret_cast<int32_t*>(w);
 
+  // single query tile and no cached norms: fuse the gallery norms into the tile stream;
+  // otherwise the norms come from the caller's cache or from one streaming pre-pass
+  const bool fuse = !g_inv_norm && p.m_tiles == 1;
   const float* gin = g_inv_norm;
-  if (!gin) {
+  if (!gin && !fuse) {
     irr_status s = row_inv_norms(g, N, D, IRR_BF16, eps, gin_ws, st);
     if (s != IRR_OK) return s;
     gin = gin_ws;
@@ -367,10 +437,17 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   if (!encode_bf16_rows(&tq, q, Q, D, BLOCK_M) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   irr_status s;
-  if (k <= 4)
-    s = launch<4, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, st);
-  else
-    s = launch<16, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, st);
+  if (fuse) {
+    if (k <= 4)
+      s = launch<4, false, true>(tq, tg, nullptr, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps, st);
+    else
+      s = launch<16, false, true>(tq, tg, nullptr, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps, st);
+  } else {
+    if (k <= 4)
+      s = launch<4, false, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps, st);
+    else
+      s = launch<16, false, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps, st);
+  }
   if (s != IRR_OK) return s;
   return merge_partials(pv, pi, p.n_chunks, Q, k, q, D, IRR_BF16, eps, idx_offset, out_val, out_idx,
                         st);
@@ -393,7 +470,7 @@ irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N
   CUtensorMap tq, tg;
   if (!encode_bf16_rows(&tq, q, Q, D, BLOCK_M) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
     return IRR_ERR_UNSUPPORTED_DEVICE;
-  return launch<4, true>(tq, tg, gin, qin, Q, N, D, 1, p, nullptr, nullptr, out_scores, st);
+  return launch<4, true, false>(tq, tg, gin, qin, Q, N, D, 1, p, nullptr, nullptr, out_scores, eps, st);
 }
 
 }  // namespace irr

@@ -1,0 +1,107 @@
+"""Secondary measurements (not the headline bench line): the fused loss kernel (BASELINE.json
+configs[2]), the fp32 exactness config (configs[1]) and the small-Q searches, each as one JSON line.
+
+    python scripts/bench_aux.py [losses] [f32] [smallq]
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+
+import imageretrievalresearch_b200 as irr
+
+PEAKS = {"hbm_gbs": 6541.1}
+p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+if os.path.exists(p):
+    PEAKS = json.load(open(p))
+
+
+def timed(fn, iters, warm=5):
+    for _ in range(warm):
+        fn(0)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        fn(i)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def losses():
+    B, D = 4096, 1536
+    for dt in (torch.float32, torch.bfloat16):
+        # 151 MB per call at fp32 is about the size of L2: rotate over 6 input sets (> 2x L2)
+        sets = [[torch.randn(B, D, device="cuda").to(dt) for _ in range(3)] for _ in range(6)]
+        ms = timed(lambda i: irr.triplet_losses_fwd_bwd(*sets[i % 6], 0.3), 60)
+        by = 6 * B * D * sets[0][0].element_size()
+        print(json.dumps({"what": "fused triplet losses fwd+bwd", "B": B, "D": D, "dtype": str(dt),
+                          "us": ms * 1e3, "algorithmic_bytes": by, "GBps": by / ms / 1e6,
+                          "hbm_frac": by / ms / 1e6 / PEAKS["hbm_gbs"],
+                          "triplets_per_s": B / (ms * 1e-3), "l2": "6 rotating input sets"}), flush=True)
+        q, p_, n = [t.clone().requires_grad_(True) for t in sets[0]]
+
+        def ag(i):
+            tl = irr.triplet_losses(q, p_, n, 0.3)
+            (tl.loss_cos + tl.loss_con).backward()
+            q.grad = p_.grad = n.grad = None
+        ms = timed(ag, 30)
+        print(json.dumps({"what": "autograd triplet losses fwd + bwd (2 kernels + torch glue)", "B": B,
+                          "dtype": str(dt), "us": ms * 1e3}), flush=True)
+    # the reference's op-by-op path on the same GPU (torch CUDA), for context
+    q, p_, n = [torch.randn(B, D, device="cuda").requires_grad_(True) for _ in range(3)]
+    cel = torch.nn.CosineEmbeddingLoss(0.3)
+    one = torch.ones(1, device="cuda")
+
+    def torch_path(i):
+        l = cel(q, p_, one) + cel(q, n, -one)
+        d1 = (p_ - q).pow(2).sum(1)
+        d0 = (n - q).pow(2).sum(1)
+        l = l + (0.5 * d1).mean() + (0.5 * torch.relu(0.3 - (d0 + 1e-9).sqrt()).pow(2)).mean()
+        l.backward()
+        q.grad = p_.grad = n.grad = None
+    ms = timed(torch_path, 30)
+    print(json.dumps({"what": "torch CUDA op-by-op losses fwd+bwd (reference's calls on the GPU)",
+                      "B": B, "us": ms * 1e3}), flush=True)
+
+
+def f32():
+    g = torch.randn(10_000, 1536, device="cuda")
+    q = torch.randn(64, 1536, device="cuda")
+    ms = timed(lambda i: irr.cosine_topk(q, g, 3), 50)
+    print(json.dumps({"what": "fp32 cosine top-3, 10k x 1536, Q=64 (configs[1])", "us": ms * 1e3,
+                      "queries_per_s": 64 / (ms * 1e-3)}), flush=True)
+    cos = torch.nn.CosineSimilarity(dim=1, eps=1e-6)
+
+    def loop(i):
+        for j in range(64):
+            torch.topk(cos(q[j].unsqueeze(0), g), 3)
+    ms = timed(loop, 5, warm=2)
+    print(json.dumps({"what": "reference loop on the same GPU (torch CUDA), 10k x 1536, Q=64",
+                      "us": ms * 1e3, "queries_per_s": 64 / (ms * 1e-3)}), flush=True)
+
+
+def smallq():
+    N, D = 1_000_000, 1536
+    g = torch.randn(N, D, device="cuda", dtype=torch.bfloat16)
+    gal = irr.Gallery(g)
+    for Q in (1, 8, 64, 128, 256, 1024, 4096):
+        q = torch.randn(Q, D, device="cuda", dtype=torch.bfloat16)
+        ms = timed(lambda i: irr.cosine_topk(q, g, 3), 20)
+        msc = timed(lambda i: gal.search(q, 3), 20)
+        by = N * D * 2 + Q * D * 2 + Q * 36
+        print(json.dumps({"what": "bf16 cosine top-3 1M x 1536", "Q": Q, "ms": ms, "ms_cached_norms": msc,
+                          "queries_per_s": Q / (ms * 1e-3), "GBps": by / ms / 1e6,
+                          "TFLOPs": 2.0 * Q * N * D / ms / 1e9}), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["losses", "f32", "smallq"]
+    for w in which:
+        globals()[w]()
