@@ -20,6 +20,7 @@
 // Every unit writes a [128, k] partial list; topk_merge.cu folds the partials, applies
 // 1/max(|q|,eps) and widens the indices.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "irr_common.cuh"
 #include "irr_kernels.h"
@@ -78,6 +79,10 @@ Plan make_plan(int64_t Q, int64_t N) {
       best_tpc = tpc;
     }
   }
+  if (const char* e = getenv("IRR_TILES_PER_CHUNK")) {  // measurement knob (profiles/), not an API
+    const int v = atoi(e);
+    if (v >= 1 && v <= p.n_tiles) best_tpc = v;
+  }
   p.tiles_per_chunk = best_tpc;
   p.n_chunks = (p.n_tiles + best_tpc - 1) / best_tpc;
   const long long units = 1ll * p.n_chunks * p.m_tiles;
@@ -97,7 +102,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         int Q, int N, int num_kb, int k, int m_tiles, int n_tiles,
                         int tiles_per_chunk, int n_chunks, float* __restrict__ part_val,
                         int32_t* __restrict__ part_idx, float* __restrict__ scores_out,
-                        uint64_t g_policy, float eps) {
+                        uint64_t g_policy, float eps, int a_rows) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -135,6 +140,16 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (a_rows < BLOCK_M) {
+    // small query batch: the TMA box only covers the first a_rows rows of each A stage; the MMA
+    // still reads 128 rows, so the rest is zeroed once here (their accumulator rows are ignored)
+    for (int s = 0; s < STAGES; ++s) {
+      uint4* a = reinterpret_cast<uint4*>(smem_gen + s * STAGE_BYTES);
+      for (int i = threadIdx.x; i < A_STAGE_BYTES / 16; i += NUM_THREADS)
+        a[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();  // generic-proxy zeros ordered before the async-proxy (TMA) writes
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -156,7 +171,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (lane == 0) {
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
             const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            mbar_arrive_expect_tx(full_bar(stage), a_rows * (BLOCK_K * 2) + B_STAGE_BYTES);
             tma_load_2d(a_dst, &tmap_q, kb * BLOCK_K, mt * BLOCK_M, full_bar(stage),
                         kPolicyEvictLast);
             tma_load_2d(b_dst, &tmap_g, kb * BLOCK_K, t * BLOCK_N, full_bar(stage), g_policy);
@@ -205,9 +220,11 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
   } else if (FUSE_NORM && warp >= NORM_WARP0) {
     // ===================== gallery-norm warps (fused-norm variant) =====================
     // thread nt owns gallery rows nt and nt+128 of the tile.  A row is 128 bytes per stage; the
-    // TMA swizzle only permutes the eight 16-byte chunks inside that row, which a sum of squares
-    // does not care about.  Chunk order is rotated by the thread index so that the eight lanes
-    // of a quarter-warp hit eight different bank groups (conflict-free LDS.128).
+    // TMA swizzle stores logical 16-byte chunk c of row r at position c ^ (r & 7).  Reading the
+    // chunks in LOGICAL order (position j ^ (r & 7)) makes the accumulation order independent of
+    // where a row sits in the gallery (duplicate rows get bit-identical norms), and because the
+    // eight lanes of a quarter-warp own eight consecutive rows they hit eight different bank
+    // groups: conflict-free LDS.128.
     const int nt = threadIdx.x - NORM_WARP0 * 32;
     int stage = 0;
     uint32_t phase = 0;
@@ -225,8 +242,8 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint4* r1 = reinterpret_cast<const uint4*>(b + (nt + NORM_THREADS) * 128);
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
-            const uint4 u0 = r0[(j + nt) & 7], u1 = r0[(j + 1 + nt) & 7];
-            const uint4 w0 = r1[(j + nt) & 7], w1 = r1[(j + 1 + nt) & 7];
+            const uint4 u0 = r0[j ^ (nt & 7)], u1 = r0[(j + 1) ^ (nt & 7)];
+            const uint4 w0 = r1[j ^ (nt & 7)], w1 = r1[(j + 1) ^ (nt & 7)];
             const uint32_t x0[4] = {u0.x, u0.y, u0.z, u0.w}, x1[4] = {u1.x, u1.y, u1.z, u1.w};
             const uint32_t y0[4] = {w0.x, w0.y, w0.z, w0.w}, y1[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
@@ -379,6 +396,12 @@ bool encode_bf16_rows(CUtensorMap* m, const void* base, int64_t rows, int64_t co
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// rows of the query TMA box: a whole 128-row tile, or for a single small batch just the rows
+// that exist (rounded up to the 8-row swizzle atom) — out-of-bounds rows cost TMA time
+int a_box_rows(int64_t Q) {
+  return Q >= BLOCK_M ? BLOCK_M : static_cast<int>((Q + 7) / 8 * 8);
+}
+
 template <int KMAX, bool WS, bool FN>
 irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, const float* qin,
                   int64_t Q, int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
@@ -393,7 +416,7 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
   kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(tq, tg, gin, qin, static_cast<int>(Q),
                                                 static_cast<int>(N), num_kb, k, p.m_tiles,
                                                 p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
-                                                scores, g_policy, eps);
+                                                scores, g_policy, eps, a_box_rows(Q));
   if (!WS) profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -434,7 +457,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
     gin = gin_ws;
   }
   CUtensorMap tq, tg;
-  if (!encode_bf16_rows(&tq, q, Q, D, BLOCK_M) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
+  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   irr_status s;
   if (fuse) {
@@ -468,7 +491,7 @@ irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N
   if (s != IRR_OK) return s;
   const Plan p = make_plan(Q, N);
   CUtensorMap tq, tg;
-  if (!encode_bf16_rows(&tq, q, Q, D, BLOCK_M) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
+  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   return launch<4, true, false>(tq, tg, gin, qin, Q, N, D, 1, p, nullptr, nullptr, out_scores, eps, st);
 }
