@@ -90,6 +90,50 @@ Plan make_plan(int64_t Q, int64_t N) {
   return p;
 }
 
+// One accumulator tile (this thread = one query row, 256 gallery columns): TMEM -> registers 32
+// columns at a time, scale by the inverse gallery norms, and fold into the row's running top-k.
+// Columns arrive in increasing gallery index, so the strict '>' insert keeps the lower index on ties.
+template <int KMAX, bool WRITE_SCORES>
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, int n0, int n_valid,
+                                              int row, int Q, int N, float qn,
+                                              float* __restrict__ scores_out,
+                                              TopKList<KMAX, int32_t>& top) {
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N; c += 32) {
+    float v[32];
+    tmem_ld_32x32(taddr + c, v);
+    tmem_ld_wait();
+    if (c >= n_valid) continue;  // warp-uniform
+    const float4* gn4 = reinterpret_cast<const float4*>(gn + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 g4 = gn4[j];
+      v[4 * j + 0] *= g4.x; v[4 * j + 1] *= g4.y;
+      v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
+    }
+    if (WRITE_SCORES) {
+      if (row < Q) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c + j < n_valid) scores_out[static_cast<size_t>(row) * N + n0 + c + j] = v[j] * qn;
+      }
+    } else {
+      if (c + 32 > n_valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c + j >= n_valid) v[j] = kNegInf;
+      }
+      float mx = kNegInf;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+      if (mx > top.v[KMAX - 1]) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) top.push_ordered(v[j], n0 + c + j);
+      }
+    }
+  }
+}
+
 // FUSE_NORM (single query tile: every gallery tile is consumed by exactly one CTA): four extra
 // warps square-sum the gallery rows out of the SAME shared-memory stages the MMA reads, so the
 // gallery crosses HBM once per search and no inverse-norm pre-pass exists.  With several query
@@ -303,42 +347,8 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_wait(tfull_bar(as), aphase, 400 + as);
         tcgen05_fence_after();
         const int n_valid = min(BLOCK_N, N - n0);
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          float v[32];
-          tmem_ld_32x32(tmem_base + lane_base + as * BLOCK_N + c, v);
-          tmem_ld_wait();
-          if (c >= n_valid) continue;  // warp-uniform
-          const float4* gn4 = reinterpret_cast<const float4*>(gn + c);
-          float mx = kNegInf;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 g4 = gn4[j];
-            v[4 * j + 0] *= g4.x; v[4 * j + 1] *= g4.y;
-            v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
-          }
-          if (WRITE_SCORES) {
-            if (row < Q) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c + j < n_valid)
-                  scores_out[static_cast<size_t>(row) * N + n0 + c + j] = v[j] * qn;
-            }
-          } else {
-            const bool full = c + 32 <= n_valid;
-            if (!full) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c + j >= n_valid) v[j] = kNegInf;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
-            if (mx > top.v[KMAX - 1]) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) top.push_ordered(v[j], n0 + c + j);
-            }
-          }
-        }
+        epilogue_tile<KMAX, WRITE_SCORES>(tmem_base + lane_base + as * BLOCK_N, gn, n0, n_valid, row,
+                                          Q, N, qn, scores_out, top);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -362,6 +372,251 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     tcgen05_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2) for batches of several query tiles.
+//
+// Two CTAs on the SMs of one TPC form a cluster and compute a 256-query x 256-gallery-row tile:
+// each CTA stages ITS 128 query rows (A) and ONE HALF (128 rows) of the gallery tile (B), the
+// leader issues M=256 MMAs that read both CTAs' shared memory, and each CTA ends up with its own
+// 128 x 256 accumulator in its own TMEM.  Per SM and k-block this moves 32 KB through shared
+// memory instead of 48 KB (the single-CTA kernel is bound by exactly that), which also buys a
+// 6-stage ring in the same 192 KB.
+//   - full barriers live in the leader; both CTAs' TMA loads complete_tx on them
+//   - tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs
+//   - both epilogues arrive on the leader's "accumulator drained" barrier
+// ---------------------------------------------------------------------------------------------
+constexpr int P_STAGES = 6;
+constexpr int P_B_ROWS = BLOCK_N / 2;                          // gallery rows staged per CTA
+constexpr int P_A_BYTES = BLOCK_M * BLOCK_K * 2;               // 16 KB
+constexpr int P_B_BYTES = P_B_ROWS * BLOCK_K * 2;              // 16 KB
+constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;           // 32 KB
+constexpr int P_SMEM_TILES = P_STAGES * P_STAGE_BYTES;         // 196608
+constexpr int P_SMEM_BARS = (2 * P_STAGES + 2 * ACC_STAGES) * 8;
+constexpr int P_SMEM_TOTAL = P_SMEM_TILES + SMEM_GN + P_SMEM_BARS + 16;
+constexpr int P_SMEM_ALLOC = P_SMEM_TOTAL + 1024;
+constexpr int P_THREADS = 256;
+
+template <int KMAX>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                             const __grid_constant__ CUtensorMap tmap_g,
+                             const float* __restrict__ g_inv_norm, int Q, int N, int num_kb, int k,
+                             int m_pairs, int n_tiles, int tiles_per_chunk, int n_chunks,
+                             float* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t bars = smem_base + P_SMEM_TILES + SMEM_GN;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (P_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + ACC_STAGES + s); };
+  const uint32_t tmem_slot = bars + P_SMEM_BARS;
+  float* gn_smem = reinterpret_cast<float*>(smem_gen + P_SMEM_TILES);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + P_SMEM_TILES + SMEM_GN + P_SMEM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();   // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_g);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);    // leader's own arrive.expect_tx; bytes come from both CTAs
+      mbar_init(empty_bar(s), 1);   // one multicast tcgen05.commit
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(tfull_bar(s), 1);                        // one multicast tcgen05.commit
+      mbar_init(tempty_bar(s), 2 * (EPI_THREADS / 32));  // 4 epilogue warps of each CTA (leader's copy)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  cluster_sync_all();   // barrier inits + TMEM allocation visible to both CTAs
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int total_units = m_pairs * n_chunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = cluster_id; u < total_units; u += num_clusters) {
+      const int chunk = u / m_pairs, mp = u - chunk * m_pairs;
+      const int mt = mp * 2 + static_cast<int>(rank);
+      const int t0 = chunk * tiles_per_chunk;
+      const int t1 = min(t0 + tiles_per_chunk, n_tiles);
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 1100 + stage);
+          if (lane == 0) {
+            const uint32_t a_dst = smem_base + stage * P_STAGE_BYTES;
+            const uint32_t b_dst = a_dst + P_A_BYTES;
+            const uint32_t lead_full = mapa_rank(full_bar(stage), 0);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * P_STAGE_BYTES);
+            tma_load_2d_pair(a_dst, &tmap_q, kb * BLOCK_K, mt * BLOCK_M, lead_full, kPolicyEvictLast);
+            tma_load_2d_pair(b_dst, &tmap_g, kb * BLOCK_K, t * BLOCK_N + static_cast<int>(rank) * P_B_ROWS,
+                             lead_full, kPolicyEvictNormal);
+          }
+          __syncwarp();
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int u = cluster_id; u < total_units; u += num_clusters) {
+        const int chunk = u / m_pairs;
+        const int t0 = chunk * tiles_per_chunk;
+        const int t1 = min(t0 + tiles_per_chunk, n_tiles);
+        for (int t = t0; t < t1; ++t, ++it) {
+          const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+          mbar_wait(tempty_bar(as), aphase ^ 1u, 1200 + as);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(full_bar(stage), phase, 1300 + stage);
+            tcgen05_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = smem_base + stage * P_STAGE_BYTES;
+              const uint64_t adesc = umma_desc_k128(a_addr);
+              const uint64_t bdesc = umma_desc_k128(a_addr + P_A_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                umma_bf16_ss_pair(tmem_d, adesc + 2u * kk, bdesc + 2u * kk, idesc,
+                                  (kb > 0 || kk > 0) ? 1u : 0u);
+              umma_commit_pair(empty_bar(stage), 0x3);
+              if (kb == num_kb - 1) umma_commit_pair(tfull_bar(as), 0x3);
+            }
+            __syncwarp();
+            if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue (both CTAs: own 128 query rows x 256 columns) ==========
+    const int ew = warp - EPI_WARP0;
+    const int et = threadIdx.x - EPI_WARP0 * 32;
+    const int row_in_tile = ew * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+    TopKList<KMAX, int32_t> top;
+    uint32_t it = 0;
+    for (int u = cluster_id; u < total_units; u += num_clusters) {
+      const int chunk = u / m_pairs, mp = u - chunk * m_pairs;
+      const int mt = mp * 2 + static_cast<int>(rank);
+      const int t0 = chunk * tiles_per_chunk;
+      const int t1 = min(t0 + tiles_per_chunk, n_tiles);
+      const int row = mt * BLOCK_M + row_in_tile;
+      top.reset();
+      for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        const int n0 = t * BLOCK_N;
+        float* gn = gn_smem + as * BLOCK_N;
+        {
+          const int c0 = n0 + et, c1 = n0 + et + EPI_THREADS;
+          gn[et] = c0 < N ? __ldg(g_inv_norm + c0) : 0.0f;
+          gn[et + EPI_THREADS] = c1 < N ? __ldg(g_inv_norm + c1) : 0.0f;
+        }
+        named_bar_sync(1, EPI_THREADS);
+        mbar_wait(tfull_bar(as), aphase, 1400 + as);
+        tcgen05_fence_after();
+        const int n_valid = min(BLOCK_N, N - n0);
+        epilogue_tile<KMAX, false>(tmem_base + lane_base + as * BLOCK_N, gn, n0, n_valid, row, Q, N,
+                                   1.0f, nullptr, top);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));
+      }
+      if (row < Q) {
+        const size_t o = (static_cast<size_t>(chunk) * Q + row) * k;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          if (j < k) {
+            part_val[o + j] = top.v[j];
+            part_idx[o + j] = top.i[j];
+          }
+        }
+      }
+    }
+  }
+
+  // neither CTA may leave (or free TMEM) while its partner can still read its shared memory,
+  // multicast to its barriers or arrive remotely
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+  }
+}
+
+// chunking for the pair kernel: units = (query-tile pair, gallery chunk) over sms/2 clusters
+Plan make_plan_pair(int64_t Q, int64_t N) {
+  Plan p;
+  const int clusters = num_sms() / 2;
+  p.m_tiles = static_cast<int>((Q + 2 * BLOCK_M - 1) / (2 * BLOCK_M));  // pairs of query tiles
+  p.n_tiles = static_cast<int>((N + BLOCK_N - 1) / BLOCK_N);
+  if (p.n_tiles < 1) p.n_tiles = 1;
+  int best_tpc = 1;
+  double best_cost = 1e300;
+  const int max_tpc = p.n_tiles < 64 ? p.n_tiles : 64;
+  for (int tpc = 1; tpc <= max_tpc; ++tpc) {
+    const int chunks = (p.n_tiles + tpc - 1) / tpc;
+    const long long units = 1ll * chunks * p.m_tiles;
+    const long long waves = (units + clusters - 1) / clusters;
+    const double cost = static_cast<double>(waves) * (tpc + 0.35);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_tpc = tpc; }
+  }
+  if (const char* e = getenv("IRR_TILES_PER_CHUNK")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= p.n_tiles) best_tpc = v;
+  }
+  p.tiles_per_chunk = best_tpc;
+  p.n_chunks = (p.n_tiles + best_tpc - 1) / best_tpc;
+  const long long units = 1ll * p.n_chunks * p.m_tiles;
+  p.grid = 2 * static_cast<int>(units < clusters ? units : clusters);
+  return p;
+}
+
+// pair kernel for two or more query tiles (IRR_NO_PAIR=1 forces the single-CTA kernel: a
+// measurement knob for profiles/, not an API)
+bool use_pair(int64_t Q) {
+  if (Q <= BLOCK_M) return false;
+  const char* e = getenv("IRR_NO_PAIR");
+  return !(e && e[0] == '1');
+}
+
+template <int KMAX>
+irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, int64_t Q,
+                       int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
+                       cudaStream_t st) {
+  auto kern = cosine_topk_bf16_pair_kernel<KMAX>;
+  IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
+  const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
+  profile_mark_start(st);
+  kern<<<p.grid, P_THREADS, P_SMEM_ALLOC, st>>>(tq, tg, gin, static_cast<int>(Q), static_cast<int>(N),
+                                                num_kb, k, p.m_tiles, p.n_tiles, p.tiles_per_chunk,
+                                                p.n_chunks, pv, pi);
+  profile_mark_stop(st);
+  IRR_LAUNCH_CHECK();
+  return IRR_OK;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -426,7 +681,7 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
 
 // workspace: [g_inv_norm fp32 N][part_val fp32 chunks*Q*k][part_idx i32 chunks*Q*k]
 size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
-  const Plan p = make_plan(Q, N);
+  const Plan p = use_pair(Q) ? make_plan_pair(Q, N) : make_plan(Q, N);
   const size_t parts = static_cast<size_t>(p.n_chunks) * Q * k;
   return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 + 256;
 }
@@ -438,7 +693,8 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   if (device_cc() / 10 != 10) return IRR_ERR_UNSUPPORTED_DEVICE;
   if (N > 0x7fffff00ll || Q > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
   if (ws_bytes < bf16_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
-  const Plan p = make_plan(Q, N);
+  const bool pair = use_pair(Q);
+  const Plan p = pair ? make_plan_pair(Q, N) : make_plan(Q, N);
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* gin_ws = reinterpret_cast<float*>(w);
   w += align_up(static_cast<size_t>(N) * 4, 256);
@@ -449,7 +705,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
 
   // single query tile and no cached norms: fuse the gallery norms into the tile stream;
   // otherwise the norms come from the caller's cache or from one streaming pre-pass
-  const bool fuse = !g_inv_norm && p.m_tiles == 1;
+  const bool fuse = !g_inv_norm && !pair && p.m_tiles == 1;
   const float* gin = g_inv_norm;
   if (!gin && !fuse) {
     irr_status s = row_inv_norms(g, N, D, IRR_BF16, eps, gin_ws, st);
@@ -457,10 +713,16 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
     gin = gin_ws;
   }
   CUtensorMap tq, tg;
-  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
+  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) ||
+      !encode_bf16_rows(&tg, g, N, D, pair ? P_B_ROWS : BLOCK_N))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   irr_status s;
-  if (fuse) {
+  if (pair) {
+    if (k <= 4)
+      s = launch_pair<4>(tq, tg, gin, Q, N, D, k, p, pv, pi, st);
+    else
+      s = launch_pair<16>(tq, tg, gin, Q, N, D, k, p, pv, pi, st);
+  } else if (fuse) {
     if (k <= 4)
       s = launch<4, false, true>(tq, tg, nullptr, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps, st);
     else
