@@ -595,12 +595,17 @@ Plan make_plan_pair(int64_t Q, int64_t N) {
   return p;
 }
 
-// pair kernel for two or more query tiles (IRR_NO_PAIR=1 forces the single-CTA kernel: a
-// measurement knob for profiles/, not an API)
+// The pair kernel takes over in the tensor-bound regime (four or more query tiles; the HBM/tensor
+// crossover is Q ~ 250).  Measured on B200 both kernels sit at the power-capped cuBLAS-sustained
+// level at Q=4096 (profiles/r01_notes.md); the pair kernel moves a third less data per flop.
+// IRR_NO_PAIR=1 / IRR_FORCE_PAIR=1 are measurement knobs for profiles/, not an API.
 bool use_pair(int64_t Q) {
   if (Q <= BLOCK_M) return false;
-  const char* e = getenv("IRR_NO_PAIR");
-  return !(e && e[0] == '1');
+  const char* no = getenv("IRR_NO_PAIR");
+  if (no && no[0] == '1') return false;
+  const char* force = getenv("IRR_FORCE_PAIR");
+  if (force && force[0] == '1') return true;
+  return Q > 3 * BLOCK_M;
 }
 
 template <int KMAX>
