@@ -308,7 +308,8 @@ def run_b200(a):
         ach = bytes_alg / (kernel_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic}
-    roof.update({"kernel": "cosine_topk_bf16_kernel", "kernel_ms": kernel_ms, "peak_source": peaks["source"],
+    kname = "cosine_topk_bf16_pair_kernel" if Q > 384 else "cosine_topk_bf16_kernel"
+    roof.update({"kernel": kname, "kernel_ms": kernel_ms, "peak_source": peaks["source"],
                  "kernel_share_of_step": kernel_ms / ms_step,
                  "algorithmic": {"flops": flops, "bytes": bytes_alg}})
 

@@ -126,6 +126,21 @@ def smallq():
                           "TFLOPs": 2.0 * Q * N * D / ms / 1e9}), flush=True)
 
 
+
+
+def config5():
+    """One GPU's share of BASELINE.json configs[4]: 10M x 2560 bf16 over 8 GPUs -> 1.25M rows per
+    GPU, Q=8192, k=10."""
+    N, D, Q, k = 1_250_000, 2560, 8192, 10
+    g = torch.randn(N, D, device="cuda", dtype=torch.bfloat16)
+    q = torch.randn(Q, D, device="cuda", dtype=torch.bfloat16)
+    ms = timed(lambda i: irr.cosine_topk(q, g, k), 5, warm=2)
+    fl = 2.0 * Q * N * D
+    print(json.dumps({"what": "bf16 cosine top-10, 1.25M x 2560 shard, Q=8192 (configs[4] per GPU)",
+                      "ms": ms, "TFLOPs": fl / ms / 1e9, "frac_burst": fl / ms / 1e9 / PEAKS["bf16_tflops"],
+                      "queries_per_s_per_gpu_shard": Q / (ms * 1e-3)}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["losses", "f32", "smallq"]
     for w in which:
