@@ -9,13 +9,15 @@ not on a CUDA device.
 from ._lib import IRR_MAX_K, IrrError, LIB_PATH, load as load_library
 from .losses import (ContrastiveLoss, CosineEmbeddingLoss, TripletFwdBwd, TripletLosses,
                      triplet_losses, triplet_losses_fwd_bwd)
-from .retrieval import CosineSimilarity, Gallery, TopK, cosine_topk, top1_top3, topk_hits
+from .retrieval import (CosineSimilarity, DedupTopK, Gallery, TopK, class_dedup_topk, cosine_topk,
+                        top1_top3, top1_top3_dedup, topk_hits)
 from .sharded import ShardedGallery, exchange_candidates, shard_bounds
 
 __all__ = [
     "IRR_MAX_K", "IrrError", "LIB_PATH", "load_library",
     "ContrastiveLoss", "CosineEmbeddingLoss", "TripletLosses", "TripletFwdBwd",
     "triplet_losses", "triplet_losses_fwd_bwd",
-    "CosineSimilarity", "Gallery", "TopK", "cosine_topk", "top1_top3", "topk_hits",
+    "CosineSimilarity", "Gallery", "TopK", "DedupTopK", "cosine_topk", "top1_top3", "topk_hits",
+    "class_dedup_topk", "top1_top3_dedup",
     "ShardedGallery", "exchange_candidates", "shard_bounds",
 ]

@@ -12,7 +12,8 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libirr_b200.so"
 
 IRR_F32, IRR_BF16 = 0, 1
-IRR_MAX_K = 16
+IRR_MAX_K = 256
+IRR_MAX_K_FUSED = 16
 IRR_ROW_STATS = 8
 IRR_LOSS_COSINE_EMBEDDING, IRR_LOSS_CONTRASTIVE = 1, 2
 
@@ -29,7 +30,10 @@ SIGNATURES = {
     "irr_cosine_scores_bf16": (_i32, [_vp, _vp, _i64, _i64, _i32, _f32, _vp, _vp, _sz, _vp]),
     "irr_row_inv_norms": (_i32, [_vp, _i64, _i32, _i32, _f32, _vp, _vp]),
     "irr_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "irr_topk_merge_strided": (_i32, [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
     "irr_topk_hits": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "irr_topk_class_dedup": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
+                                    _vp]),
     "irr_pair_cosine": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _vp]),
     "irr_triplet_loss_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "irr_triplet_loss_fwd_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32, _f32,

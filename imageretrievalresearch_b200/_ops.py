@@ -96,14 +96,18 @@ def row_inv_norms(x: torch.Tensor, eps: float) -> torch.Tensor:
 
 
 def cosine_topk_raw(q: torch.Tensor, g: torch.Tensor, k: int, eps: float,
-                    g_inv_norm: Optional[torch.Tensor], idx_offset: int
+                    g_inv_norm: Optional[torch.Tensor], idx_offset: int,
+                    out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
                     ) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     Q, D = q.shape
     N = g.shape[0]
     dt = dtype_code(q)
-    vals = torch.empty((Q, k), dtype=torch.float32, device=q.device)
-    idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+    if out is None:
+        vals = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+        idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+    else:
+        vals, idx = out
     with torch.cuda.device(q.device):
         need = lib.irr_cosine_topk_workspace_bytes(Q, N, D, k, dt)
         ws = scratch(q.device, need)
@@ -149,6 +153,21 @@ def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor) -> Tuple[torch.Te
     return vals, idx
 
 
+def topk_merge_packed(gathered: torch.Tensor, G: int, Q: int, k: int, idx_byte_offset: int,
+                      rank_bytes: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge straight out of an all-gather receive buffer of G packed messages
+    [fp32 scores Q*k | pad | int64 indices Q*k] (no unpack copies)."""
+    lib = _lib.load()
+    vals = torch.empty((Q, k), dtype=torch.float32, device=gathered.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=gathered.device)
+    base = gathered.data_ptr()
+    with torch.cuda.device(gathered.device):
+        check(lib.irr_topk_merge_strided(base, rank_bytes // 4, base + idx_byte_offset,
+                                         rank_bytes // 8, G, Q, k, ptr(vals), ptr(idx),
+                                         stream_ptr(gathered.device)), "irr_topk_merge_strided")
+    return vals, idx
+
+
 def topk_hits(idx: torch.Tensor, q_label: Optional[torch.Tensor], g_label: Optional[torch.Tensor],
               instance_offset: int) -> torch.Tensor:
     lib = _lib.load()
@@ -167,6 +186,33 @@ def topk_hits(idx: torch.Tensor, q_label: Optional[torch.Tensor], g_label: Optio
         check(lib.irr_topk_hits(ptr(idx), Q, k, ptr(q_label), ptr(g_label), N, instance_offset,
                                 ptr(out), stream_ptr(idx.device)), "irr_topk_hits")
     return out
+
+
+def class_dedup(vals: torch.Tensor, idx: torch.Tensor, g_label: torch.Tensor, n_distinct: int,
+                q_label: Optional[torch.Tensor]):
+    lib = _lib.load()
+    _require_cuda(idx, "indices")
+    dev = idx.device
+    vals = vals.to(device=dev, dtype=torch.float32).contiguous()
+    idx = idx.contiguous().long()
+    g_label = g_label.to(device=dev, dtype=torch.int64).contiguous()
+    Q, k = idx.shape
+    if vals.shape != idx.shape:
+        raise ValueError("values / indices must have the same [Q, k] shape")
+    hits = None
+    if q_label is not None:
+        q_label = q_label.to(device=dev, dtype=torch.int64).contiguous()
+        if q_label.numel() != Q:
+            raise ValueError(f"query_labels has {q_label.numel()} entries for {Q} queries")
+        hits = torch.empty(2, dtype=torch.int64, device=dev)
+    out_l = torch.empty((Q, n_distinct), dtype=torch.int64, device=dev)
+    out_i = torch.empty((Q, n_distinct), dtype=torch.int64, device=dev)
+    out_v = torch.empty((Q, n_distinct), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.irr_topk_class_dedup(ptr(vals), ptr(idx), Q, k, ptr(g_label), g_label.numel(),
+                                       n_distinct, ptr(q_label), ptr(out_l), ptr(out_i), ptr(out_v),
+                                       ptr(hits), stream_ptr(dev)), "irr_topk_class_dedup")
+    return out_l, out_i, out_v, hits
 
 
 def pair_cosine(x1: torch.Tensor, x2: torch.Tensor, eps: float) -> torch.Tensor:

@@ -763,4 +763,17 @@ irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N
   return launch<4, true, false>(tq, tg, gin, qin, Q, N, D, 1, p, nullptr, nullptr, out_scores, eps, st);
 }
 
+// dense [Q,N] cosine scores with both inverse norms supplied (a block of the large-k path)
+irr_status bf16_scores_block(const void* q, const void* g, const float* g_inv_norm,
+                             const float* q_inv_norm, int64_t Q, int64_t N, int32_t D, float eps,
+                             float* out_scores, cudaStream_t st) {
+  if (device_cc() / 10 != 10) return IRR_ERR_UNSUPPORTED_DEVICE;
+  const Plan p = make_plan(Q, N);
+  CUtensorMap tq, tg;
+  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
+    return IRR_ERR_UNSUPPORTED_DEVICE;
+  return launch<4, true, false>(tq, tg, g_inv_norm, q_inv_norm, Q, N, D, 1, p, nullptr, nullptr,
+                                out_scores, eps, st);
+}
+
 }  // namespace irr

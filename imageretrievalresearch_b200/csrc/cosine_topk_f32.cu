@@ -47,12 +47,15 @@ Plan make_plan(int64_t Q, int64_t N) {
   return p;
 }
 
-template <int KMAX>
+// WRITE_SCORES: instead of selecting, publish the dense cosine tile (both norms applied) — the
+// first stage of the large-k path (topk_select.cu).
+template <int KMAX, bool WRITE_SCORES>
 __global__ void __launch_bounds__(THREADS, 2)
 cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
                        const float* __restrict__ g_inv_norm, int Q, int N, int D, int k,
                        int m_tiles, int n_tiles, int tiles_per_chunk,
-                       float* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+                       float* __restrict__ part_val, int32_t* __restrict__ part_idx,
+                       const float* __restrict__ q_inv_norm, float* __restrict__ scores_out) {
   extern __shared__ __align__(16) uint8_t smem[];
   float* As = reinterpret_cast<float*>(smem);                      // [2][BK][A_LD]
   float* Bs = reinterpret_cast<float*>(smem + SMEM_A);             // [2][BK][B_LD]
@@ -160,13 +163,20 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
         Ss[(ty * 4 + i) * S_LD + c] = acc[i][j] * gn[j];
       }
     __syncthreads();
-    if (t < BM) {
+    if (WRITE_SCORES) {
+      for (int e = t; e < BM * BN; e += THREADS) {
+        const int r = e / BN, c = e - r * BN;
+        if (m0 + r < Q && n0 + c < N)
+          scores_out[static_cast<size_t>(m0 + r) * N + n0 + c] =
+              Ss[r * S_LD + c] * __ldg(q_inv_norm + m0 + r);
+      }
+    } else if (t < BM) {
       const int n_valid = min(BN, N - n0);
       const float* s = Ss + t * S_LD;
       for (int c = 0; c < n_valid; ++c) top.push_ordered(s[c], n0 + c);
     }
   }
-  if (t < BM && m0 + t < Q) {
+  if (!WRITE_SCORES && t < BM && m0 + t < Q) {
     const size_t o = (static_cast<size_t>(chunk) * Q + m0 + t) * k;
 #pragma unroll
     for (int j = 0; j < KMAX; ++j)
@@ -209,21 +219,38 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
   const int grid = p.m_tiles * p.n_chunks;
   profile_mark_start(st);
   if (k <= 4) {
-    auto kern = cosine_topk_f32_kernel<4>;
+    auto kern = cosine_topk_f32_kernel<4, false>;
     IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(static_cast<const float*>(q), static_cast<const float*>(g),
                                             gin, static_cast<int>(Q), static_cast<int>(N), D, k,
-                                            p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi);
+                                            p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi,
+                                            nullptr, nullptr);
   } else {
-    auto kern = cosine_topk_f32_kernel<16>;
+    auto kern = cosine_topk_f32_kernel<16, false>;
     IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(static_cast<const float*>(q), static_cast<const float*>(g),
                                             gin, static_cast<int>(Q), static_cast<int>(N), D, k,
-                                            p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi);
+                                            p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi,
+                                            nullptr, nullptr);
   }
   profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return merge_partials(pv, pi, p.n_chunks, Q, k, q, D, IRR_F32, eps, idx_offset, out_val, out_idx, st);
+}
+
+// dense [Q,N] cosine scores (both norms applied) for the large-k path; g_inv_norm / q_inv_norm given
+irr_status f32_cosine_scores(const void* q, const void* g, const float* g_inv_norm,
+                             const float* q_inv_norm, int64_t Q, int64_t N, int32_t D,
+                             float* out_scores, cudaStream_t st) {
+  const Plan p = make_plan(Q, N);
+  auto kern = cosine_topk_f32_kernel<4, true>;
+  IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  kern<<<p.m_tiles * p.n_chunks, THREADS, SMEM_BYTES, st>>>(
+      static_cast<const float*>(q), static_cast<const float*>(g), g_inv_norm, static_cast<int>(Q),
+      static_cast<int>(N), D, 1, p.m_tiles, p.n_tiles, p.tiles_per_chunk, nullptr, nullptr,
+      q_inv_norm, out_scores);
+  IRR_LAUNCH_CHECK();
+  return IRR_OK;
 }
 
 }  // namespace irr

@@ -55,6 +55,58 @@ irr_status check_rows(const void* p, int32_t D, irr_dtype dt) {
   return IRR_OK;
 }
 
+// ---- large-k path (IRR_MAX_K_FUSED < k <= IRR_MAX_K): dense score blocks + row-wise selection ----
+constexpr size_t kScoreBlockBudget = size_t(1) << 30;   // bytes of scores materialised at a time
+
+int64_t large_k_block_rows(int64_t Q, int64_t N) {
+  int64_t qb = static_cast<int64_t>(kScoreBlockBudget / (static_cast<size_t>(N > 0 ? N : 1) * 4));
+  if (qb < 1) qb = 1;
+  if (qb >= 128) qb = qb / 128 * 128;
+  return qb < Q ? qb : Q;
+}
+
+size_t large_k_workspace_bytes(int64_t Q, int64_t N) {
+  return align_up(static_cast<size_t>(N) * 4, 256) + align_up(static_cast<size_t>(Q) * 4, 256) +
+         align_up(static_cast<size_t>(large_k_block_rows(Q, N)) * N * 4, 256) + 256;
+}
+
+irr_status large_k_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
+                               int64_t N, int32_t D, int32_t k, irr_dtype dt, float eps,
+                               int64_t idx_offset, float* out_val, int64_t* out_idx, void* ws,
+                               size_t ws_bytes, cudaStream_t st) {
+  if (N > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
+  if (ws_bytes < large_k_workspace_bytes(Q, N)) return IRR_ERR_WORKSPACE_TOO_SMALL;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  float* gin_ws = reinterpret_cast<float*>(w);
+  w += align_up(static_cast<size_t>(N) * 4, 256);
+  float* qin = reinterpret_cast<float*>(w);
+  w += align_up(static_cast<size_t>(Q) * 4, 256);
+  float* scores = reinterpret_cast<float*>(w);
+  const float* gin = g_inv_norm;
+  irr_status s;
+  if (!gin) {
+    s = row_inv_norms(g, N, D, dt, eps, gin_ws, st);
+    if (s != IRR_OK) return s;
+    gin = gin_ws;
+  }
+  s = row_inv_norms(q, Q, D, dt, eps, qin, st);
+  if (s != IRR_OK) return s;
+  const int64_t qb = large_k_block_rows(Q, N);
+  const size_t row_bytes = static_cast<size_t>(D) * dtype_bytes(dt);
+  for (int64_t b0 = 0; b0 < Q; b0 += qb) {
+    const int64_t rows = b0 + qb <= Q ? qb : Q - b0;
+    const void* qblk = static_cast<const uint8_t*>(q) + b0 * row_bytes;
+    if (dt == IRR_BF16)
+      s = bf16_scores_block(qblk, g, gin, qin + b0, rows, N, D, eps, scores, st);
+    else
+      s = f32_cosine_scores(qblk, g, gin, qin + b0, rows, N, D, scores, st);
+    if (s != IRR_OK) return s;
+    s = topk_select(scores, rows, N, k, idx_offset, out_val + b0 * k, out_idx + b0 * k, st);
+    if (s != IRR_OK) return s;
+  }
+  return IRR_OK;
+}
+
 }  // namespace
 }  // namespace irr
 
@@ -86,6 +138,7 @@ const char* irr_status_string(irr_status s) {
 size_t irr_cosine_topk_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t k, irr_dtype dt) {
   (void)D;
   if (Q < 0 || N < 0 || k < 1) return 0;
+  if (k > IRR_MAX_K_FUSED) return large_k_workspace_bytes(Q, N);
   return dt == IRR_BF16 ? bf16_topk_workspace_bytes(Q, N, k) : f32_topk_workspace_bytes(Q, N, k);
 }
 
@@ -102,6 +155,9 @@ irr_status irr_cosine_topk(const void* q, const void* g, const float* g_inv_norm
   s = check_rows(g, D, dt);
   if (s != IRR_OK) return s;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (k > IRR_MAX_K_FUSED)
+    return large_k_cosine_topk(q, g, g_inv_norm, Q, N, D, k, dt, eps, idx_offset, out_val, out_idx,
+                               workspace, workspace_bytes, st);
   if (dt == IRR_BF16)
     return bf16_cosine_topk(q, g, g_inv_norm, Q, N, D, k, eps, idx_offset, out_val, out_idx,
                             workspace, workspace_bytes, st);
@@ -134,8 +190,20 @@ irr_status irr_topk_merge(const float* cand_val, const int64_t* cand_idx, int32_
   if (G < 1 || Q < 0 || k < 1 || !cand_val || !cand_idx || !out_val || !out_idx)
     return IRR_ERR_INVALID_ARG;
   if (k > IRR_MAX_K) return IRR_ERR_K_TOO_LARGE;
-  return merge_candidates(cand_val, cand_idx, G, Q, k, out_val, out_idx,
+  return merge_candidates(cand_val, Q * k, cand_idx, Q * k, G, Q, k, out_val, out_idx,
                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_topk_merge_strided(const float* cand_val, int64_t val_rank_stride,
+                                  const int64_t* cand_idx, int64_t idx_rank_stride, int32_t G,
+                                  int64_t Q, int32_t k, float* out_val, int64_t* out_idx,
+                                  irr_stream_t stream) {
+  if (G < 1 || Q < 0 || k < 1 || !cand_val || !cand_idx || !out_val || !out_idx)
+    return IRR_ERR_INVALID_ARG;
+  if (val_rank_stride < Q * k || idx_rank_stride < Q * k) return IRR_ERR_INVALID_ARG;
+  if (k > IRR_MAX_K) return IRR_ERR_K_TOO_LARGE;
+  return merge_candidates(cand_val, val_rank_stride, cand_idx, idx_rank_stride, G, Q, k, out_val,
+                          out_idx, reinterpret_cast<cudaStream_t>(stream));
 }
 
 irr_status irr_topk_hits(const int64_t* idx, int64_t Q, int32_t k, const int64_t* q_label,
@@ -145,6 +213,18 @@ irr_status irr_topk_hits(const int64_t* idx, int64_t Q, int32_t k, const int64_t
   if ((q_label == nullptr) != (g_label == nullptr)) return IRR_ERR_INVALID_ARG;
   return topk_hits(idx, Q, k, q_label, g_label, N, instance_offset, out_hits,
                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_topk_class_dedup(const float* val, const int64_t* idx, int64_t Q, int32_t k,
+                                const int64_t* g_label, int64_t N, int32_t n_distinct,
+                                const int64_t* q_label, int64_t* out_label, int64_t* out_idx,
+                                float* out_val, int64_t* out_hits, irr_stream_t stream) {
+  if (Q < 0 || k < 1 || N < 0 || !g_label || !out_label || !out_idx || !out_val ||
+      (Q > 0 && (!val || !idx)))
+    return IRR_ERR_INVALID_ARG;
+  if (out_hits && !q_label) return IRR_ERR_INVALID_ARG;
+  return class_dedup(val, idx, Q, k, g_label, N, n_distinct, q_label, out_label, out_idx, out_val,
+                     out_hits, reinterpret_cast<cudaStream_t>(stream));
 }
 
 irr_status irr_pair_cosine(const void* x1, int64_t x1_rows, const void* x2, int64_t N, int32_t D,

@@ -26,8 +26,9 @@ irr_status pair_cosine(const void* x1, int64_t x1_rows, const void* x2, int64_t 
 irr_status merge_partials(const float* part_val, const int32_t* part_idx, int32_t S, int64_t Q,
                           int32_t k, const void* q, int32_t D, irr_dtype dt, float eps,
                           int64_t idx_offset, float* out_val, int64_t* out_idx, cudaStream_t st);
-irr_status merge_candidates(const float* cand_val, const int64_t* cand_idx, int32_t G, int64_t Q,
-                            int32_t k, float* out_val, int64_t* out_idx, cudaStream_t st);
+irr_status merge_candidates(const float* cand_val, int64_t val_rank_stride, const int64_t* cand_idx,
+                            int64_t idx_rank_stride, int32_t G, int64_t Q, int32_t k,
+                            float* out_val, int64_t* out_idx, cudaStream_t st);
 irr_status topk_hits(const int64_t* idx, int64_t Q, int32_t k, const int64_t* q_label,
                      const int64_t* g_label, int64_t N, int64_t instance_offset, int64_t* out_hits,
                      cudaStream_t st);
@@ -42,12 +43,32 @@ irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N
                               float eps, float* out_scores, void* ws, size_t ws_bytes,
                               cudaStream_t st);
 
+irr_status bf16_scores_block(const void* q, const void* g, const float* g_inv_norm,
+                             const float* q_inv_norm, int64_t Q, int64_t N, int32_t D, float eps,
+                             float* out_scores, cudaStream_t st);
+
+// topk_select.cu (large k: select from a dense score block; class de-duplication)
+irr_status topk_select(const float* scores, int64_t Q, int64_t N, int32_t k, int64_t idx_offset,
+                       float* out_val, int64_t* out_idx, cudaStream_t st);
+irr_status merge_candidates_large(const float* cand_val, int64_t val_rank_stride,
+                                  const int64_t* cand_idx, int64_t idx_rank_stride, int32_t G,
+                                  int64_t Q, int32_t k, float* out_val, int64_t* out_idx,
+                                  cudaStream_t st);
+irr_status class_dedup(const float* val, const int64_t* idx, int64_t Q, int32_t k,
+                       const int64_t* g_label, int64_t N, int32_t n_distinct, const int64_t* q_label,
+                       int64_t* out_label, int64_t* out_idx, float* out_val, int64_t* out_hits,
+                       cudaStream_t st);
+
 // cosine_topk_f32.cu (fp32 FFMA, exactness path)
 size_t f32_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k);
 irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
                            int64_t N, int32_t D, int32_t k, float eps, int64_t idx_offset,
                            float* out_val, int64_t* out_idx, void* ws, size_t ws_bytes,
                            cudaStream_t st);
+
+irr_status f32_cosine_scores(const void* q, const void* g, const float* g_inv_norm,
+                             const float* q_inv_norm, int64_t Q, int64_t N, int32_t D,
+                             float* out_scores, cudaStream_t st);
 
 // triplet_loss.cu
 struct LossArgs {

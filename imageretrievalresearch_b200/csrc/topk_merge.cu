@@ -63,8 +63,9 @@ merge_partials_kernel(const float* __restrict__ part_val, const int32_t* __restr
 
 template <int KMAX>
 __global__ void __launch_bounds__(THREADS)
-merge_candidates_kernel(const float* __restrict__ cand_val, const int64_t* __restrict__ cand_idx,
-                        int G, int64_t Q, int k, float* __restrict__ out_val,
+merge_candidates_kernel(const float* __restrict__ cand_val, int64_t val_rank_stride,
+                        const int64_t* __restrict__ cand_idx, int64_t idx_rank_stride, int G,
+                        int64_t Q, int k, float* __restrict__ out_val,
                         int64_t* __restrict__ out_idx) {
   const int lane = threadIdx.x & 31;
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * WARPS + (threadIdx.x >> 5);
@@ -74,8 +75,9 @@ merge_candidates_kernel(const float* __restrict__ cand_val, const int64_t* __res
   const int total = G * k;
   for (int c = lane; c < total; c += 32) {
     const int g = c / k, j = c - g * k;
-    const size_t o = (static_cast<size_t>(g) * Q + qi) * k + j;
-    L.push_any(__ldg(cand_val + o), static_cast<long long>(__ldg(cand_idx + o)));
+    const size_t o = static_cast<size_t>(qi) * k + j;
+    L.push_any(__ldg(cand_val + g * val_rank_stride + o),
+               static_cast<long long>(__ldg(cand_idx + g * idx_rank_stride + o)));
   }
   warp_merge_topk<KMAX, long long>(L, k, [&](int j, float v, long long i) {
     if (lane == 0) {
@@ -133,14 +135,20 @@ irr_status merge_partials(const float* part_val, const int32_t* part_idx, int32_
   return IRR_OK;
 }
 
-irr_status merge_candidates(const float* cand_val, const int64_t* cand_idx, int32_t G, int64_t Q,
-                            int32_t k, float* out_val, int64_t* out_idx, cudaStream_t st) {
+irr_status merge_candidates(const float* cand_val, int64_t val_rank_stride, const int64_t* cand_idx,
+                            int64_t idx_rank_stride, int32_t G, int64_t Q, int32_t k,
+                            float* out_val, int64_t* out_idx, cudaStream_t st) {
   if (Q == 0) return IRR_OK;
+  if (k > IRR_MAX_K_FUSED)
+    return merge_candidates_large(cand_val, val_rank_stride, cand_idx, idx_rank_stride, G, Q, k,
+                                  out_val, out_idx, st);
   const int grid = static_cast<int>((Q + WARPS - 1) / WARPS);
   if (k <= 4)
-    merge_candidates_kernel<4><<<grid, THREADS, 0, st>>>(cand_val, cand_idx, G, Q, k, out_val, out_idx);
+    merge_candidates_kernel<4><<<grid, THREADS, 0, st>>>(cand_val, val_rank_stride, cand_idx,
+                                                         idx_rank_stride, G, Q, k, out_val, out_idx);
   else
-    merge_candidates_kernel<16><<<grid, THREADS, 0, st>>>(cand_val, cand_idx, G, Q, k, out_val, out_idx);
+    merge_candidates_kernel<16><<<grid, THREADS, 0, st>>>(cand_val, val_rank_stride, cand_idx,
+                                                          idx_rank_stride, G, Q, k, out_val, out_idx);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
 }

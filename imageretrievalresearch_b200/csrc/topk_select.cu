@@ -1,0 +1,244 @@
+// topk_select.cu — large-k selection (16 < k <= 256) and the notebook's class de-duplication.
+//
+// Replaces   vals, inds = torch.topk(cos(fm, fms_poss_all), k=150)            ipynb:238
+// and        the "first 3 distinct classes among the top-150" loop + top1/top3   ipynb:240-251
+// of inference/training_analysis.ipynb (the reference's working inference evaluation).
+//
+// k = 150 sorted entries per query row do not fit a register-resident epilogue, so the large-k path
+// is two stages: the cosine kernels publish a dense score block [Qb, N] (Qb bounded by the
+// workspace), and this kernel selects per row.  One CTA per row streams the row once with a running
+// threshold (the current k-th best): survivors — rare after the first few thousand columns — are
+// appended to a shared-memory buffer and folded into the sorted best-256 list by a bitonic sort of
+// 1024 packed 64-bit keys  (orderable(score) << 32 | ~index), so that one unsigned compare gives
+// "score descending, ties -> lower index".
+#include "irr_common.cuh"
+#include "irr_kernels.h"
+
+namespace irr {
+namespace {
+
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_BEST = 256;                 // sorted best list (>= k)
+constexpr int SEL_KEYS = 1024;                // best + candidate buffer, power of two for the sort
+constexpr int SEL_CHUNK = 2 * SEL_THREADS;    // columns scanned between flush checks
+constexpr int SEL_FLUSH_AT = SEL_KEYS - SEL_BEST - SEL_CHUNK;  // 256: buffer can take one more chunk
+
+__device__ __forceinline__ uint32_t orderable(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ unsigned long long make_key(float v, uint32_t idx) {
+  return (static_cast<unsigned long long>(orderable(v)) << 32) | (0xffffffffu - idx);
+}
+
+// descending bitonic sort of SEL_KEYS keys by SEL_THREADS threads
+__device__ __forceinline__ void sort_keys_desc(unsigned long long* keys) {
+  for (int size = 2; size <= SEL_KEYS; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < SEL_KEYS / 2; t += SEL_THREADS) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+topk_select_kernel(const float* __restrict__ scores, int64_t N, int k, int64_t idx_offset,
+                   float* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+  __shared__ unsigned long long keys[SEL_KEYS];
+  __shared__ int count;
+  const int64_t row = blockIdx.x;
+  const float* s = scores + row * N;
+  for (int i = threadIdx.x; i < SEL_KEYS; i += SEL_THREADS) keys[i] = 0ull;  // 0 = padding (< any key)
+  if (threadIdx.x == 0) count = 0;
+  __syncthreads();
+  float thr = kNegInf;      // current k-th best score; nothing below it can enter
+  bool full = false;        // best list already holds k real entries
+  for (int64_t base = 0; base < N; base += SEL_CHUNK) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t c = base + h * SEL_THREADS + threadIdx.x;
+      if (c < N) {
+        const float v = __ldg(s + c);
+        // columns arrive in increasing index: a later column equal to the threshold loses the tie
+        if (!full ? (v == v) : (v > thr)) {
+          const int pos = atomicAdd(&count, 1);
+          keys[SEL_BEST + pos] = make_key(v, static_cast<uint32_t>(c));
+        }
+      }
+    }
+    __syncthreads();
+    if (count > SEL_FLUSH_AT || base + SEL_CHUNK >= N) {
+      sort_keys_desc(keys);
+      for (int i = SEL_BEST + threadIdx.x; i < SEL_KEYS; i += SEL_THREADS) keys[i] = 0ull;
+      if (threadIdx.x == 0) count = 0;
+      const unsigned long long kth = keys[k - 1];
+      full = kth != 0ull;
+      thr = full ? from_orderable(static_cast<uint32_t>(kth >> 32)) : kNegInf;
+      __syncthreads();
+    }
+  }
+  for (int j = threadIdx.x; j < k; j += SEL_THREADS) {
+    const unsigned long long key = keys[j];
+    const bool real = key != 0ull;
+    out_val[row * k + j] = real ? from_orderable(static_cast<uint32_t>(key >> 32)) : kNegInf;
+    out_idx[row * k + j] =
+        real ? static_cast<int64_t>(0xffffffffu - static_cast<uint32_t>(key)) + idx_offset : -1;
+  }
+}
+
+// Cross-shard merge for large k: G*k <= 2048 candidates per query, one CTA per query, bitonic sort
+// of (score, int64 index) pairs with the full comparator (score desc, index asc, padding last).
+constexpr int MRG_SLOTS = 2048;
+
+__device__ __forceinline__ bool before(float va, long long ia, float vb, long long ib) {
+  if (ia < 0 || ib < 0) return ia >= 0 && ib < 0;   // real entries before padding
+  return va > vb || (va == vb && ia < ib);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+merge_large_kernel(const float* __restrict__ cand_val, int64_t val_rank_stride,
+                   const int64_t* __restrict__ cand_idx, int64_t idx_rank_stride, int G, int64_t Q,
+                   int k, float* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+  __shared__ float sv[MRG_SLOTS];
+  __shared__ long long si[MRG_SLOTS];
+  const int64_t qi = blockIdx.x;
+  const int total = G * k;
+  for (int c = threadIdx.x; c < MRG_SLOTS; c += SEL_THREADS) {
+    if (c < total) {
+      const int g = c / k, j = c - g * k;
+      const size_t o = static_cast<size_t>(qi) * k + j;
+      sv[c] = __ldg(cand_val + g * val_rank_stride + o);
+      si[c] = static_cast<long long>(__ldg(cand_idx + g * idx_rank_stride + o));
+    } else {
+      sv[c] = kNegInf;
+      si[c] = -1;
+    }
+  }
+  for (int size = 2; size <= MRG_SLOTS; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < MRG_SLOTS / 2; t += SEL_THREADS) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool first_half = (lo & size) == 0;   // this half sorts "best first"
+        const float va = sv[lo], vb = sv[hi];
+        const long long ia = si[lo], ib = si[hi];
+        const bool swap = first_half ? before(vb, ib, va, ia) : before(va, ia, vb, ib);
+        if (swap) { sv[lo] = vb; sv[hi] = va; si[lo] = ib; si[hi] = ia; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += SEL_THREADS) {
+    const bool real = si[j] >= 0;
+    out_val[qi * k + j] = real ? sv[j] : kNegInf;
+    out_idx[qi * k + j] = real ? si[j] : -1;
+  }
+}
+
+constexpr int DEDUP_MAX = 8;
+
+// one thread per query: walk its ranked list, keep the first n distinct labels (ipynb:243-249)
+__global__ void __launch_bounds__(128)
+class_dedup_kernel(const float* __restrict__ val, const int64_t* __restrict__ idx, int64_t Q, int k,
+                   const int64_t* __restrict__ g_label, int64_t N, int n_distinct,
+                   const int64_t* __restrict__ q_label, int64_t* __restrict__ out_label,
+                   int64_t* __restrict__ out_idx, float* __restrict__ out_val,
+                   unsigned long long* __restrict__ out_hits) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  unsigned long long h1 = 0, hn = 0;
+  if (i < Q) {
+    int64_t lab[DEDUP_MAX];
+    int found = 0;
+    for (int j = 0; j < k && found < n_distinct; ++j) {
+      const int64_t g = idx[i * k + j];
+      if (g < 0 || g >= N) continue;
+      const int64_t l = g_label[g];
+      bool seen = false;
+#pragma unroll
+      for (int m = 0; m < DEDUP_MAX; ++m) seen |= (m < found && lab[m] == l);
+      if (!seen) {
+#pragma unroll
+        for (int m = 0; m < DEDUP_MAX; ++m)
+          if (m == found) lab[m] = l;
+        out_label[i * n_distinct + found] = l;
+        out_idx[i * n_distinct + found] = g;
+        out_val[i * n_distinct + found] = val[i * k + j];
+        ++found;
+      }
+    }
+    for (int m = found; m < n_distinct; ++m) {
+      out_label[i * n_distinct + m] = -1;
+      out_idx[i * n_distinct + m] = -1;
+      out_val[i * n_distinct + m] = kNegInf;
+    }
+    if (q_label) {
+      const int64_t want = q_label[i];
+      bool any = false;
+#pragma unroll
+      for (int m = 0; m < DEDUP_MAX; ++m) any |= (m < found && lab[m] == want);
+      h1 = (found > 0 && lab[0] == want) ? 1 : 0;
+      hn = any ? 1 : 0;
+    }
+  }
+  if (out_hits) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+      hn += __shfl_xor_sync(0xffffffffu, hn, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (h1) atomicAdd(out_hits + 0, h1);
+      if (hn) atomicAdd(out_hits + 1, hn);
+    }
+  }
+}
+
+}  // namespace
+
+irr_status topk_select(const float* scores, int64_t Q, int64_t N, int32_t k, int64_t idx_offset,
+                       float* out_val, int64_t* out_idx, cudaStream_t st) {
+  if (Q == 0) return IRR_OK;
+  topk_select_kernel<<<static_cast<unsigned>(Q), SEL_THREADS, 0, st>>>(scores, N, k, idx_offset,
+                                                                       out_val, out_idx);
+  IRR_LAUNCH_CHECK();
+  return IRR_OK;
+}
+
+irr_status merge_candidates_large(const float* cand_val, int64_t val_rank_stride,
+                                  const int64_t* cand_idx, int64_t idx_rank_stride, int32_t G,
+                                  int64_t Q, int32_t k, float* out_val, int64_t* out_idx,
+                                  cudaStream_t st) {
+  if (static_cast<int64_t>(G) * k > MRG_SLOTS) return IRR_ERR_K_TOO_LARGE;
+  if (Q == 0) return IRR_OK;
+  merge_large_kernel<<<static_cast<unsigned>(Q), SEL_THREADS, 0, st>>>(
+      cand_val, val_rank_stride, cand_idx, idx_rank_stride, G, Q, k, out_val, out_idx);
+  IRR_LAUNCH_CHECK();
+  return IRR_OK;
+}
+
+irr_status class_dedup(const float* val, const int64_t* idx, int64_t Q, int32_t k,
+                       const int64_t* g_label, int64_t N, int32_t n_distinct, const int64_t* q_label,
+                       int64_t* out_label, int64_t* out_idx, float* out_val, int64_t* out_hits,
+                       cudaStream_t st) {
+  if (n_distinct < 1 || n_distinct > DEDUP_MAX) return IRR_ERR_INVALID_ARG;
+  if (out_hits) IRR_CUDA_TRY(cudaMemsetAsync(out_hits, 0, 2 * sizeof(int64_t), st));
+  if (Q == 0) return IRR_OK;
+  class_dedup_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, st>>>(
+      val, idx, Q, k, g_label, N, n_distinct, q_label, out_label, out_idx, out_val,
+      reinterpret_cast<unsigned long long*>(out_hits));
+  IRR_LAUNCH_CHECK();
+  return IRR_OK;
+}
+
+}  // namespace irr

@@ -55,7 +55,8 @@ class CosineSimilarity(torch.nn.Module):
 
 def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, eps: float = 1e-6, *,
                 gallery_inv_norm: Optional[torch.Tensor] = None, idx_offset: int = 0,
-                allow_short: bool = False) -> TopK:
+                allow_short: bool = False,
+                out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> TopK:
     """Fused ``topk(cos(q_i[None], gallery), k)`` for every query row.
 
     Row ``i`` of the result is what the reference's per-query loop yields for query ``i``:
@@ -67,6 +68,7 @@ def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, eps: float
     gallery_inv_norm: cached ``1/max(|g|, eps)`` per gallery row (see :class:`Gallery`).
     idx_offset: added to the returned indices (first row of this shard).
     allow_short: a shard with fewer than ``k`` rows pads with (-inf, -1) instead of raising.
+    out: optional preallocated contiguous (values fp32 [Q,k], indices int64 [Q,k]) to write into.
     """
     q, g = _ops.as_rows(queries, "queries"), _ops.as_rows(gallery, "gallery")
     _ops.check_same(q, g, "queries", "gallery")
@@ -80,7 +82,13 @@ def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, eps: float
         gallery_inv_norm = gallery_inv_norm.to(device=g.device, dtype=torch.float32).contiguous()
         if gallery_inv_norm.numel() != g.shape[0]:
             raise ValueError("gallery_inv_norm must have one entry per gallery row")
-    vals, idx = _ops.cosine_topk_raw(q, g, k, eps, gallery_inv_norm, idx_offset)
+    if out is not None:
+        ov, oi = out
+        if (ov.shape != (q.shape[0], k) or oi.shape != (q.shape[0], k) or ov.dtype != torch.float32
+                or oi.dtype != torch.int64 or not ov.is_contiguous() or not oi.is_contiguous()
+                or ov.device != q.device or oi.device != q.device):
+            raise ValueError("out must be contiguous (fp32 [Q,k], int64 [Q,k]) on the query device")
+    vals, idx = _ops.cosine_topk_raw(q, g, k, eps, gallery_inv_norm, idx_offset, out)
     return TopK(vals, idx)
 
 
@@ -113,6 +121,37 @@ def top1_top3(queries: torch.Tensor, gallery: torch.Tensor,
     return frac[0], frac[1], res
 
 
+class DedupTopK(NamedTuple):
+    labels: torch.Tensor            # [Q, n] int64: first n distinct labels in rank order (-1 pad)
+    indices: torch.Tensor           # [Q, n] int64: gallery row each label was first seen at
+    values: torch.Tensor            # [Q, n] fp32: its cosine score
+    hits: Optional[torch.Tensor]    # int64[2] (top1, topn) when query labels were given
+
+
+def class_dedup_topk(topk: TopK, gallery_labels: torch.Tensor, n_distinct: int = 3,
+                     query_labels: Optional[torch.Tensor] = None) -> DedupTopK:
+    """The notebook's class de-duplication (inference/training_analysis.ipynb:240-251): walk each
+    query's ranked list and keep the first ``n_distinct`` DISTINCT gallery labels; with
+    ``query_labels`` also count top1 (label equals the first distinct label) and topn (label among
+    them), on the device."""
+    if not 1 <= n_distinct <= 8:
+        raise ValueError("n_distinct must be in 1..8")
+    l, i, v, h = _ops.class_dedup(topk.values, topk.indices, gallery_labels, n_distinct, query_labels)
+    return DedupTopK(l, i, v, h)
+
+
+def top1_top3_dedup(queries: torch.Tensor, gallery: torch.Tensor, query_labels: torch.Tensor,
+                    gallery_labels: torch.Tensor, *, k: int = 150, n_distinct: int = 3,
+                    eps: float = 1e-6) -> Tuple[torch.Tensor, torch.Tensor, DedupTopK]:
+    """The working inference evaluation of the reference (ipynb:231-257) without the per-query
+    Python loop: top-``k`` (150) cosine rows per query, first 3 distinct classes, top1 / top3 as
+    hits / Q (0-d fp32 device tensors)."""
+    res = cosine_topk(queries, gallery, min(k, gallery.shape[0]), eps)
+    d = class_dedup_topk(res, gallery_labels, n_distinct, query_labels)
+    frac = d.hits.to(torch.float32) / float(res.indices.shape[0])
+    return frac[0], frac[1], d
+
+
 class Gallery:
     """A resident gallery shard: embeddings plus cached inverse row norms.
 
@@ -132,6 +171,7 @@ class Gallery:
     def num_rows(self) -> int:
         return self.embeddings.shape[0]
 
-    def search(self, queries: torch.Tensor, k: int, allow_short: bool = False) -> TopK:
+    def search(self, queries: torch.Tensor, k: int, allow_short: bool = False,
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> TopK:
         return cosine_topk(queries, self.embeddings, k, self.eps, gallery_inv_norm=self.inv_norm,
-                           idx_offset=self.first_row, allow_short=allow_short)
+                           idx_offset=self.first_row, allow_short=allow_short, out=out)

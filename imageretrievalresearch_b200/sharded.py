@@ -29,7 +29,8 @@ def shard_bounds(total_rows: int, world_size: int, rank: int) -> Tuple[int, int]
 
 
 def _packed_layout(Q: int, k: int) -> Tuple[int, int]:
-    """(byte offset of the int64 indices, total bytes) of one rank's packed candidate message."""
+    """(byte offset of the int64 indices, total bytes) of one rank's packed candidate message:
+    [fp32 scores Q*k | pad to 8 B | int64 indices Q*k], total a multiple of 8."""
     val_bytes = Q * k * 4
     off = (val_bytes + 7) // 8 * 8
     return off, off + Q * k * 8
@@ -92,9 +93,18 @@ class ShardedGallery:
     def search(self, queries: torch.Tensor, k: int) -> TopK:
         if k > self.total_rows:
             raise RuntimeError("selected index k out of range")
-        local = self.local.search(queries, k, allow_short=True)
         if self.world == 1:
-            return local
-        cand_val, cand_idx = exchange_candidates(local.values, local.indices, self.group)
-        vals, idx = _ops.topk_merge(cand_val, cand_idx)
-        return TopK(vals, idx)
+            return self.local.search(queries, k, allow_short=True)
+        # the local top-k writes straight into this rank's packed message, ONE all-gather moves
+        # the G messages, and the merge kernel reads them in place (irr_topk_merge_strided)
+        Q = queries.shape[0]
+        off, total = _packed_layout(Q, k)
+        dev = self.local.embeddings.device
+        msg = torch.empty(total, dtype=torch.uint8, device=dev)
+        vals = msg[: Q * k * 4].view(torch.float32).view(Q, k)
+        idx = msg[off:].view(torch.int64).view(Q, k)
+        self.local.search(queries, k, allow_short=True, out=(vals, idx))
+        gathered = torch.empty(self.world * total, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, msg, group=self.group)
+        mv, mi = _ops.topk_merge_packed(gathered, self.world, Q, k, off, total)
+        return TopK(mv, mi)

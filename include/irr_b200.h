@@ -56,8 +56,11 @@ enum {
 
 typedef enum { IRR_F32 = 0, IRR_BF16 = 1 } irr_dtype;
 
-/* largest k the register-resident top-k epilogues keep per query row */
-#define IRR_MAX_K 16
+/* largest k of irr_cosine_topk; up to IRR_MAX_K_FUSED the register-resident epilogues select inside
+ * the GEMM kernel (scores never written), above it a dense score block of bounded size is
+ * materialised in the workspace and selected row-wise (the notebook's k=150) */
+#define IRR_MAX_K 256
+#define IRR_MAX_K_FUSED 16
 
 /* which losses a pair/triplet call evaluates (bit mask) */
 enum { IRR_LOSS_COSINE_EMBEDDING = 1, IRR_LOSS_CONTRASTIVE = 2 };
@@ -85,7 +88,7 @@ IRR_API const char* irr_status_string(irr_status s);
  * out_val [Q,k] fp32 sorted descending, ties broken by LOWER gallery index;
  * out_idx [Q,k] int64 = local row index + idx_offset (idx_offset = first row of this shard).
  * Slots beyond N (k > N) hold (-inf, -1).   1 <= k <= IRR_MAX_K.
- * The Q x N score matrix is never written to memory.
+ * For k <= IRR_MAX_K_FUSED the Q x N score matrix is never written to memory.
  * ------------------------------------------------------------------------------------------ */
 IRR_API size_t irr_cosine_topk_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t k,
                                                irr_dtype dt);
@@ -121,6 +124,15 @@ IRR_API irr_status irr_topk_merge(const float* cand_val, const int64_t* cand_idx
                                   int64_t Q, int32_t k, float* out_val, int64_t* out_idx,
                                   irr_stream_t stream);
 
+/* Same merge reading each rank's lists in place from an all-gather receive buffer: rank g's scores
+ * start at cand_val + g*val_rank_stride (floats), its indices at cand_idx + g*idx_rank_stride
+ * (int64s); both strides >= Q*k.  Lets the exchange be one collective on a packed message with no
+ * pack / unpack copies. */
+IRR_API irr_status irr_topk_merge_strided(const float* cand_val, int64_t val_rank_stride,
+                                          const int64_t* cand_idx, int64_t idx_rank_stride,
+                                          int32_t G, int64_t Q, int32_t k, float* out_val,
+                                          int64_t* out_idx, irr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * top-1 / top-k hit accounting — replaces the per-row Python tests
  *   class flavour    train/train_efficient_cos_con_ce_loss.py:279-281,390-392
@@ -133,6 +145,21 @@ IRR_API irr_status irr_topk_merge(const float* cand_val, const int64_t* cand_idx
 IRR_API irr_status irr_topk_hits(const int64_t* idx, int64_t Q, int32_t k, const int64_t* q_label,
                                  const int64_t* g_label, int64_t N, int64_t instance_offset,
                                  int64_t* out_hits, irr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Class de-duplication of a ranked list — replaces the notebook's loop that walks the top-150
+ * and keeps the first 3 DISTINCT classes, then counts top1 / top3
+ *   inference/training_analysis.ipynb:240-251
+ * val/idx [Q,k] (output of irr_cosine_topk), g_label int64[N], 1 <= n_distinct <= 8.
+ * out_label / out_idx / out_val [Q,n_distinct]: the distinct labels in rank order, the gallery row
+ * each was first seen at, and its score; unused slots hold (-1, -1, -inf).
+ * q_label (optional) + out_hits int64[2] (optional): {#q_label == first label, #q_label among them}.
+ * ------------------------------------------------------------------------------------------ */
+IRR_API irr_status irr_topk_class_dedup(const float* val, const int64_t* idx, int64_t Q, int32_t k,
+                                        const int64_t* g_label, int64_t N, int32_t n_distinct,
+                                        const int64_t* q_label, int64_t* out_label,
+                                        int64_t* out_idx, float* out_val, int64_t* out_hits,
+                                        irr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row-wise cosine similarity — replaces cos(x1, x2) itself:

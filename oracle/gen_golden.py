@@ -102,6 +102,32 @@ def golden_retrieval():
             top1 += 1
     out.update(batch_q=tq.numpy(), batch_p=tp.numpy(), batch_clss=clss.numpy(),
                batch_vals=torch.stack(v10).numpy(), batch_top1=np.int64(top1), batch_top3=np.int64(top3))
+    # notebook flavour (ipynb:231-251): top-150 + first 3 distinct classes, gallery = all positives
+    gq, gp, _ = synthetic.triplets(420, 64, seed=51)
+    cls = torch.arange(420) // 70                      # 6 classes x 70 rows, like Sketchy's ~70 / class
+    centers = torch.randn(6, 64, generator=torch.Generator().manual_seed(52))
+    gq = gq + 0.22 * synthetic.unit(centers)[cls]
+    gp = gp * 0 + synthetic.unit(torch.randn(420, 64, generator=torch.Generator().manual_seed(54))) + 0.22 * synthetic.unit(centers)[cls] + 0.05 * torch.randn(420, 64, generator=torch.Generator().manual_seed(53))
+    nb_top1 = nb_top3 = 0
+    nb_r, nb_i, nb_v, nb_vals150 = [], [], [], []
+    for idx, (gt_reg, fm) in enumerate(zip(cls, gq)):
+        vals, inds = torch.topk(cos(fm, gp), k=150)
+        nb_vals150.append(vals)
+        classes = [int(cls[int(ind)]) for ind in inds]
+        top_i, top_v, top_r = [], [], []
+        for num, (i, v, r) in enumerate(zip(inds, vals, classes)):
+            if r not in top_r:
+                top_r.append(r); top_v.append(float(v)); top_i.append(int(i))
+            if len(top_r) == 3:
+                break
+        nb_top3 += 1 if int(gt_reg) in top_r else 0
+        nb_top1 += 1 if int(gt_reg) == top_r[0] else 0
+        pad = 3 - len(top_r)
+        nb_r.append(top_r + [-1] * pad); nb_i.append(top_i + [-1] * pad); nb_v.append(top_v + [float("-inf")] * pad)
+    out.update(nb_q=gq.numpy(), nb_p=gp.numpy(), nb_cls=cls.numpy(), nb_top1=np.int64(nb_top1),
+               nb_top3=np.int64(nb_top3), nb_r=np.array(nb_r, dtype=np.int64),
+               nb_i=np.array(nb_i, dtype=np.int64), nb_v=np.array(nb_v, dtype=np.float32),
+               nb_vals150=torch.stack(nb_vals150).numpy())
     # iid gallery, k=10: values only (index order near ties is torch.topk's business)
     q2, g2 = synthetic.iid_gallery(N=1000, D=72, Q=6, seed=41)
     v = torch.stack([torch.topk(cos(q2[i].unsqueeze(0), g2), k=10)[0] for i in range(6)])

@@ -125,6 +125,56 @@ def hits_from_indices(indices: torch.Tensor, q_label: Optional[torch.Tensor],
     return int(m[:, 0].sum()), int(m.any(dim=1).sum())
 
 
+def class_dedup_loop(fms_ims_all: torch.Tensor, fms_poss_all: torch.Tensor, classes_all: torch.Tensor,
+                     k: int = 150, n_distinct: int = 3, eps: float = COS_EPS):
+    """The notebook's working inference evaluation, verbatim (inference/training_analysis.ipynb:
+    231-251): per query top-k (150) by cosine, walk the ranked rows, keep the first 3 distinct
+    classes; top3 / top1 by class.  Returns (top1 count, top3 count, top_r lists, top_i lists,
+    top_v lists).  Tie order inside torch.topk is torch's own."""
+    cos = torch.nn.CosineSimilarity(dim=1, eps=eps)                               # ipynb:187
+    top1 = top3 = 0
+    top_r_list, top_inds, top_vals = [], [], []
+    for idx, (gt_reg, fm) in enumerate(zip(classes_all, fms_ims_all)):            # :231
+        vals, inds = torch.topk(cos(fm, fms_poss_all), k=k)                       # :238
+        classes = [int(classes_all[int(ind)]) for ind in inds]                    # :240
+        top_i, top_v, top_r = [], [], []
+        for num, (i, v, r) in enumerate(zip(inds, vals, classes)):                # :243
+            if r not in top_r:
+                top_r.append(r)
+                top_v.append(float(v))
+                top_i.append(int(i))
+            if len(top_r) == n_distinct:
+                break
+        top3 += 1 if int(gt_reg) in top_r else 0                                  # :250
+        top1 += 1 if int(gt_reg) == top_r[0] else 0                               # :251
+        top_inds.append(top_i)
+        top_vals.append(top_v)
+        top_r_list.append(top_r)
+    return top1, top3, top_r_list, top_inds, top_vals
+
+
+def class_dedup_from_ranked(indices: torch.Tensor, values: torch.Tensor, g_label: torch.Tensor,
+                            n_distinct: int = 3):
+    """ipynb:240-249 applied to already-ranked lists: [Q,n] labels / indices / values, -1 / -inf pad."""
+    Q = indices.shape[0]
+    lab = torch.full((Q, n_distinct), -1, dtype=torch.int64)
+    ind = torch.full((Q, n_distinct), -1, dtype=torch.int64)
+    val = torch.full((Q, n_distinct), -float("inf"), dtype=torch.float32)
+    for q in range(Q):
+        seen = []
+        for j in range(indices.shape[1]):
+            g = int(indices[q, j])
+            if g < 0:
+                continue
+            r = int(g_label[g])
+            if r not in seen:
+                lab[q, len(seen)], ind[q, len(seen)], val[q, len(seen)] = r, g, float(values[q, j])
+                seen.append(r)
+            if len(seen) == n_distinct:
+                break
+    return lab, ind, val
+
+
 # -------------------------------------------------------------------------------------------------
 # a4  paired scores
 # -------------------------------------------------------------------------------------------------

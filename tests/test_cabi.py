@@ -70,7 +70,7 @@ def test_argument_validation_without_a_device():
     # null pointers
     assert lib.irr_cosine_topk(None, None, None, 4, 4, 8, 1, 0, 1e-6, 0, None, None, None, 0, None) == -1
     # k too large
-    assert lib.irr_cosine_topk(p16, p16, None, 4, 40, 8, 17, 1, 1e-6, 0, p16, p16, p16, 4096, None) == -5
+    assert lib.irr_cosine_topk(p16, p16, None, 4, 400, 8, 257, 1, 1e-6, 0, p16, p16, p16, 4096, None) == -5
     # D violates the 16-byte row contract (bf16 needs D % 8 == 0)
     assert lib.irr_cosine_topk(p16, p16, None, 4, 40, 12, 3, 1, 1e-6, 0, p16, p16, p16, 4096, None) == -3
     # misaligned base pointer

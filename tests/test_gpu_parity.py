@@ -237,7 +237,7 @@ def test_short_shard_and_errors():
     assert (res.indices[:, 2] == -1).all() and torch.isinf(res.values[:, 2]).all()
     assert set(res.indices[0, :2].tolist()) == {100, 101}
     with pytest.raises(ValueError):
-        irr.cosine_topk(q.cuda(), gal.cuda(), irr.IRR_MAX_K + 1)
+        irr.cosine_topk(q.cuda(), gal.cuda(), irr.IRR_MAX_K + 1, allow_short=True)
     with pytest.raises(irr.IrrError) as e:   # D=12 bf16 rows are not 16-byte multiples
         irr.cosine_topk(torch.randn(2, 12).cuda().bfloat16(), torch.randn(9, 12).cuda().bfloat16(), 1)
     assert e.value.status == -3
@@ -417,3 +417,98 @@ def test_raw_cabi_call():
     st = lib.irr_cosine_topk(qd.data_ptr(), gd.data_ptr(), None, 10, 5000, 256, 3, _lib.IRR_BF16,
                              1e-6, 0, vals.data_ptr(), idx.data_ptr(), small.data_ptr(), 16, None)
     assert st == -4
+
+
+# -------------------------------------------------------------------------------------------------
+# next row: k = 150 + class de-duplication, the notebook's working evaluation
+# -------------------------------------------------------------------------------------------------
+def test_golden_notebook_top150_dedup(golden_retrieval):
+    g = golden_retrieval
+    q, p, cls = T(g["nb_q"]), T(g["nb_p"]), T(g["nb_cls"])
+    res = irr.cosine_topk(q, p, 150)
+    want_v = T(g["nb_vals150"])
+    assert ((res.values - want_v).abs() <= FP32_REL * want_v.abs() + 1e-7).all()
+    check_topk(res, q.cpu(), p.cpu(), 150, FP32_REL, relative=True)
+    d = irr.class_dedup_topk(res, cls, 3, cls)
+    assert torch.equal(d.labels, T(g["nb_r"])) and torch.equal(d.indices, T(g["nb_i"]))
+    assert (d.values - T(g["nb_v"])).abs().max() < 1e-6
+    assert d.hits.tolist() == [int(g["nb_top1"]), int(g["nb_top3"])]
+    top1, top3, _ = irr.top1_top3_dedup(q, p, cls, cls, k=150)
+    assert abs(top1.item() * 420 - int(g["nb_top1"])) < 1e-3
+    assert abs(top3.item() * 420 - int(g["nb_top3"])) < 1e-3
+    # bf16 inputs through the tensor-core score kernel
+    rb = irr.cosine_topk(q.bfloat16(), p.bfloat16(), 150)
+    check_topk(rb, q.bfloat16().cpu(), p.bfloat16().cpu(), 150, 1e-4, relative=False)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Q,N,D,k", [(37, 8736, 1920, 150), (300, 5000, 64, 17), (5, 100, 72, 100),
+                                     (2, 40, 8, 256), (130, 20_000, 256, 256)])
+def test_large_k_select(dtype, Q, N, D, k):
+    q, gal = synthetic.tied_gallery(N, D, Q, seed=N + k, dtype=dtype)
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), k, allow_short=True)
+    kk = min(k, N)
+    tol, relative = (FP32_REL, True) if dtype == torch.float32 else (1e-4, False)
+    check_topk(res, q, gal, kk, tol, relative)
+    assert (res.values[:, :kk - 1] >= res.values[:, 1:kk]).all()
+    if k > N:
+        assert (res.indices[:, N:] == -1).all() and torch.isinf(res.values[:, N:]).all()
+    # exact duplicates: lower index first
+    assert (res.indices[:, 0] < res.indices[:, 1]).all() or N < 4
+
+
+def test_large_k_query_blocking(monkeypatch):
+    """N large enough that the score block holds fewer rows than Q (several blocks)."""
+    q, gal, pos = synthetic.planted_gallery(1_200_000, 64, 300, 3, seed=12, dtype=torch.bfloat16)
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), 20)
+    assert torch.equal(res.indices[:, :3].cpu(), pos)
+    want = torch.nn.functional.cosine_similarity(q.cuda().float().unsqueeze(1), gal.cuda()[res.indices].float(),
+                                                 dim=2, eps=1e-6)
+    assert (res.values - want).abs().max() < 1e-5
+    assert (res.values[:, :-1] >= res.values[:, 1:]).all()
+
+
+@pytest.mark.parametrize("G,Q,k", [(8, 50, 150), (4, 9, 256), (2, 33, 17)])
+def test_large_k_merge_vs_oracle(G, Q, k):
+    torch.manual_seed(G + k)
+    vals = torch.randn(G, Q, k).sort(dim=2, descending=True).values
+    idx = torch.stack([torch.randperm(5000)[:k].sort().values + g * 5000
+                       for g in range(G) for _ in range(Q)]).view(G, Q, k)
+    vals[0, :, 0] = vals[1, :, 0]
+    idx[G - 1, ::3, k - 1] = -1
+    vals[G - 1, ::3, k - 1] = -float("inf")
+    v, i = _ops.topk_merge(vals.cuda(), idx.cuda())
+    wv, wi = ref.merge_candidates(vals, idx, k)
+    assert torch.equal(i.cpu(), wi) and torch.equal(v.cpu(), wv)
+
+
+@pytest.mark.parametrize("k", [3, 150])
+def test_packed_exchange_buffer_merge(k):
+    """irr_topk_merge_strided reading the all-gather receive buffer in place (one-device emulation
+    of the G messages the sharded search exchanges)."""
+    from imageretrievalresearch_b200 import sharded
+    G, Q = 4, 21
+    torch.manual_seed(k)
+    vals = torch.randn(G, Q, k).sort(dim=2, descending=True).values
+    idx = torch.stack([torch.randperm(3000)[:k].sort().values + g * 3000
+                       for g in range(G) for _ in range(Q)]).view(G, Q, k)
+    msgs = torch.cat([sharded.pack_candidates(vals[g].cuda(), idx[g].cuda()) for g in range(G)])
+    off, total = sharded._packed_layout(Q, k)
+    v, i = _ops.topk_merge_packed(msgs, G, Q, k, off, total)
+    wv, wi = ref.merge_candidates(vals, idx, k)
+    assert torch.equal(i.cpu(), wi) and torch.equal(v.cpu(), wv)
+
+
+def test_dedup_edge_cases():
+    # fewer distinct classes than requested, padding entries, n_distinct = 1
+    idx = torch.tensor([[0, 1, 2, 3], [4, 4, 5, -1], [6, -1, -1, -1]])
+    val = torch.tensor([[.9, .8, .7, .6], [.5, .5, .4, -float("inf")], [.3] + [-float("inf")] * 3])
+    lab = torch.tensor([7, 7, 7, 9, 2, 2, 1])
+    d = irr.class_dedup_topk(irr.TopK(val.cuda(), idx.cuda()), lab.cuda(), 3, torch.tensor([9, 2, 5]).cuda())
+    assert d.labels.tolist() == [[7, 9, -1], [2, -1, -1], [1, -1, -1]]
+    assert d.indices.tolist() == [[0, 3, -1], [4, -1, -1], [6, -1, -1]]
+    assert d.hits.tolist() == [1, 2]
+    wl, wi, wv = ref.class_dedup_from_ranked(idx, val, lab, 3)
+    assert torch.equal(d.labels.cpu(), wl) and torch.equal(d.indices.cpu(), wi)
+    d1 = irr.class_dedup_topk(irr.TopK(val.cuda(), idx.cuda()), lab.cuda(), 1)
+    assert d1.labels.flatten().tolist() == [7, 2, 1] and d1.hits is None

@@ -142,3 +142,20 @@ def test_synthetic_triplets_exercise_all_branches():
         assert (l > 0).all()
     d = (n - q).pow(2).sum(1).sqrt()
     assert (d < 0.2).any() and (d > 0.5).any()
+
+
+def test_notebook_class_dedup_matches_reference(golden_retrieval):
+    """ipynb:231-251: top-150, first 3 distinct classes, top1/top3 by class."""
+    g = golden_retrieval
+    q, p, cls = T(g["nb_q"]), T(g["nb_p"]), T(g["nb_cls"])
+    top1, top3, top_r, top_i, top_v = ref.class_dedup_loop(q, p, cls, k=150)
+    assert (top1, top3) == (int(g["nb_top1"]), int(g["nb_top3"]))
+    assert 0 < top1 < top3 < 420
+    assert top_r == [[c for c in row if c >= 0] for row in g["nb_r"].tolist()]
+    assert top_i == [[c for c in row if c >= 0] for row in g["nb_i"].tolist()]
+    # the batched oracle (stable top-150 + dedup) agrees with the loop
+    sv, si, _ = ref.cos_topk_stable(q, p, 150)
+    assert (sv.float() - T(g["nb_vals150"])).abs().max() < 3e-7
+    lab, ind, val = ref.class_dedup_from_ranked(si, sv.float(), cls, 3)
+    assert torch.equal(lab, T(g["nb_r"])) and torch.equal(ind, T(g["nb_i"]))
+    assert (val - T(g["nb_v"])).abs().max() < 3e-7
