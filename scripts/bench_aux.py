@@ -141,6 +141,23 @@ def config5():
                       "queries_per_s_per_gpu_shard": Q / (ms * 1e-3)}), flush=True)
 
 
+def notebook():
+    """The reference notebook's evaluation size (inference/training_analysis.ipynb:277): 8736 queries
+    against the 8736 positives, D=1920 (rexnet_150), top-150 + class de-dup + top1/top3."""
+    Q = N = 8736
+    D = 1920
+    q = torch.randn(Q, D, device="cuda")
+    g = torch.randn(N, D, device="cuda")
+    cls = torch.arange(N, device="cuda") // 70
+    for dt in (torch.float32, torch.bfloat16):
+        qq, gg = q.to(dt), g.to(dt)
+        ms = timed(lambda i: irr.top1_top3_dedup(qq, gg, cls, cls, k=150), 5, warm=2)
+        print(json.dumps({"what": "notebook evaluation 8736 x 8736 x 1920, k=150 + class de-dup + top1/top3",
+                          "dtype": str(dt), "ms": ms, "queries_per_s": Q / (ms * 1e-3)}), flush=True)
+        ms3 = timed(lambda i: irr.top1_top3(qq, gg, cls, cls, k=3), 5, warm=2)
+        print(json.dumps({"what": "same size, fused k=3 path", "dtype": str(dt), "ms": ms3}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["losses", "f32", "smallq"]
     for w in which:
