@@ -448,8 +448,10 @@ def test_large_k_select(dtype, Q, N, D, k):
     q, gal = synthetic.tied_gallery(N, D, Q, seed=N + k, dtype=dtype)
     res = irr.cosine_topk(q.cuda(), gal.cuda(), k, allow_short=True)
     kk = min(k, N)
-    tol, relative = (FP32_REL, True) if dtype == torch.float32 else (1e-4, False)
-    check_topk(res, q, gal, kk, tol, relative)
+    # k close to N reaches scores near zero, where a relative bound is ill-conditioned (SURVEY §7
+    # hard part ii): use the equivalent absolute bound for |score| <= 1
+    tol = 2e-6 if dtype == torch.float32 else 1e-4
+    check_topk(res, q, gal, kk, tol, relative=False)
     assert (res.values[:, :kk - 1] >= res.values[:, 1:kk]).all()
     if k > N:
         assert (res.indices[:, N:] == -1).all() and torch.isinf(res.values[:, N:]).all()
