@@ -93,11 +93,13 @@ Plan make_plan(int64_t Q, int64_t N) {
 // One accumulator tile (this thread = one query row, 256 gallery columns): TMEM -> registers 32
 // columns at a time, scale by the inverse gallery norms, and fold into the row's running top-k.
 // Columns arrive in increasing gallery index, so the strict '>' insert keeps the lower index on ties.
+// `floor` is a lower bound on this row's final k-th best score published by other gallery chunks
+// (row_floor[], see below): anything strictly below it can be dropped without looking at the list.
 template <int KMAX, bool WRITE_SCORES>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, int n0, int n_valid,
                                               int row, int Q, int N, float qn,
                                               float* __restrict__ scores_out,
-                                              TopKList<KMAX, int32_t>& top) {
+                                              TopKList<KMAX, int32_t>& top, float floor) {
 #pragma unroll 1
   for (int c = 0; c < BLOCK_N; c += 32) {
     float v[32];
@@ -126,12 +128,33 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, i
       float mx = kNegInf;
 #pragma unroll
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
-      if (mx > top.v[KMAX - 1]) {
+      // warp-uniform skips: first the whole 32-column group, then each column
+      if (__any_sync(0xffffffffu, mx > top.v[KMAX - 1] && mx >= floor)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) top.push_ordered(v[j], n0 + c + j);
+        for (int j = 0; j < 32; ++j) {
+          const bool take = v[j] > top.v[KMAX - 1] && v[j] >= floor;
+          if (__any_sync(0xffffffffu, take)) top.insert_ranked(take, v[j], n0 + c + j);
+        }
       }
     }
   }
+}
+
+// row_floor[Q]: orderable(k-th best score) each row has reached in ANY gallery chunk so far
+// (0 = none yet; zeroed before every launch).  Chunks of the same rows run on other CTAs at the same
+// time or earlier; reading the floor once per tile lets every chunk start with a warm threshold
+// instead of re-learning it, which removes almost all insert work for larger k.  Exactness: the
+// floor is the KMAX-th best of a subset, hence <= the final k-th best; only scores strictly below
+// it are dropped.
+__device__ __forceinline__ float read_floor(const uint32_t* row_floor, int row, int Q) {
+  if (row >= Q) return kNegInf;
+  const uint32_t u = __ldcg(row_floor + row);
+  return u ? from_orderable(u) : kNegInf;
+}
+template <int KMAX>
+__device__ __forceinline__ void publish_floor(uint32_t* row_floor, int row, int Q,
+                                              const TopKList<KMAX, int32_t>& top, float floor) {
+  if (row < Q && top.v[KMAX - 1] > floor) atomicMax(row_floor + row, orderable(top.v[KMAX - 1]));
 }
 
 // FUSE_NORM (single query tile: every gallery tile is consumed by exactly one CTA): four extra
@@ -146,7 +169,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         int Q, int N, int num_kb, int k, int m_tiles, int n_tiles,
                         int tiles_per_chunk, int n_chunks, float* __restrict__ part_val,
                         int32_t* __restrict__ part_idx, float* __restrict__ scores_out,
-                        uint64_t g_policy, float eps, int a_rows) {
+                        uint64_t g_policy, float eps, int a_rows, uint32_t* __restrict__ row_floor) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -347,8 +370,10 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_wait(tfull_bar(as), aphase, 400 + as);
         tcgen05_fence_after();
         const int n_valid = min(BLOCK_N, N - n0);
+        const float floor = WRITE_SCORES ? kNegInf : read_floor(row_floor, row, Q);
         epilogue_tile<KMAX, WRITE_SCORES>(tmem_base + lane_base + as * BLOCK_N, gn, n0, n_valid, row,
-                                          Q, N, qn, scores_out, top);
+                                          Q, N, qn, scores_out, top, floor);
+        if (!WRITE_SCORES) publish_floor<KMAX>(row_floor, row, Q, top, floor);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -404,7 +429,8 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                              const __grid_constant__ CUtensorMap tmap_g,
                              const float* __restrict__ g_inv_norm, int Q, int N, int num_kb, int k,
                              int m_pairs, int n_tiles, int tiles_per_chunk, int n_chunks,
-                             float* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+                             float* __restrict__ part_val, int32_t* __restrict__ part_idx,
+                             uint32_t* __restrict__ row_floor) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -538,8 +564,10 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_wait(tfull_bar(as), aphase, 1400 + as);
         tcgen05_fence_after();
         const int n_valid = min(BLOCK_N, N - n0);
+        const float floor = read_floor(row_floor, row, Q);
         epilogue_tile<KMAX, false>(tmem_base + lane_base + as * BLOCK_N, gn, n0, n_valid, row, Q, N,
-                                   1.0f, nullptr, top);
+                                   1.0f, nullptr, top, floor);
+        publish_floor<KMAX>(row_floor, row, Q, top, floor);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));
@@ -611,14 +639,14 @@ bool use_pair(int64_t Q) {
 template <int KMAX>
 irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, int64_t Q,
                        int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
-                       cudaStream_t st) {
+                       uint32_t* row_floor, cudaStream_t st) {
   auto kern = cosine_topk_bf16_pair_kernel<KMAX>;
   IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
   const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
   profile_mark_start(st);
   kern<<<p.grid, P_THREADS, P_SMEM_ALLOC, st>>>(tq, tg, gin, static_cast<int>(Q), static_cast<int>(N),
                                                 num_kb, k, p.m_tiles, p.n_tiles, p.tiles_per_chunk,
-                                                p.n_chunks, pv, pi);
+                                                p.n_chunks, pv, pi, row_floor);
   profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -665,7 +693,7 @@ int a_box_rows(int64_t Q) {
 template <int KMAX, bool WS, bool FN>
 irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, const float* qin,
                   int64_t Q, int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
-                  float* scores, float eps, cudaStream_t st) {
+                  float* scores, float eps, uint32_t* row_floor, cudaStream_t st) {
   auto kern = cosine_topk_bf16_kernel<KMAX, WS, FN>;
   IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
   const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
@@ -676,7 +704,7 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
   kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(tq, tg, gin, qin, static_cast<int>(Q),
                                                 static_cast<int>(N), num_kb, k, p.m_tiles,
                                                 p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
-                                                scores, g_policy, eps, a_box_rows(Q));
+                                                scores, g_policy, eps, a_box_rows(Q), row_floor);
   if (!WS) profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -684,11 +712,12 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
 
 }  // namespace
 
-// workspace: [g_inv_norm fp32 N][part_val fp32 chunks*Q*k][part_idx i32 chunks*Q*k]
+// workspace: [g_inv_norm fp32 N][part_val fp32 chunks*Q*k][part_idx i32 chunks*Q*k][row_floor u32 Q]
 size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
   const Plan p = use_pair(Q) ? make_plan_pair(Q, N) : make_plan(Q, N);
   const size_t parts = static_cast<size_t>(p.n_chunks) * Q * k;
-  return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 + 256;
+  return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 +
+         align_up(static_cast<size_t>(Q) * 4, 256) + 256;
 }
 
 irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
@@ -707,6 +736,9 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   float* pv = reinterpret_cast<float*>(w);
   w += align_up(parts * 4, 256);
   int32_t* pi = reinterpret_cast<int32_t*>(w);
+  w += align_up(parts * 4, 256);
+  uint32_t* row_floor = reinterpret_cast<uint32_t*>(w);
+  IRR_CUDA_TRY(cudaMemsetAsync(row_floor, 0, static_cast<size_t>(Q) * 4, st));
 
   // single query tile and no cached norms: fuse the gallery norms into the tile stream;
   // otherwise the norms come from the caller's cache or from one streaming pre-pass
@@ -724,19 +756,23 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   irr_status s;
   if (pair) {
     if (k <= 4)
-      s = launch_pair<4>(tq, tg, gin, Q, N, D, k, p, pv, pi, st);
+      s = launch_pair<4>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, st);
     else
-      s = launch_pair<16>(tq, tg, gin, Q, N, D, k, p, pv, pi, st);
+      s = launch_pair<16>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, st);
   } else if (fuse) {
     if (k <= 4)
-      s = launch<4, false, true>(tq, tg, nullptr, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps, st);
+      s = launch<4, false, true>(tq, tg, nullptr, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps,
+                                 row_floor, st);
     else
-      s = launch<16, false, true>(tq, tg, nullptr, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps, st);
+      s = launch<16, false, true>(tq, tg, nullptr, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps,
+                                  row_floor, st);
   } else {
     if (k <= 4)
-      s = launch<4, false, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps, st);
+      s = launch<4, false, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps,
+                                  row_floor, st);
     else
-      s = launch<16, false, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps, st);
+      s = launch<16, false, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps,
+                                   row_floor, st);
   }
   if (s != IRR_OK) return s;
   return merge_partials(pv, pi, p.n_chunks, Q, k, q, D, IRR_BF16, eps, idx_offset, out_val, out_idx,
@@ -760,7 +796,8 @@ irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N
   CUtensorMap tq, tg;
   if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
     return IRR_ERR_UNSUPPORTED_DEVICE;
-  return launch<4, true, false>(tq, tg, gin, qin, Q, N, D, 1, p, nullptr, nullptr, out_scores, eps, st);
+  return launch<4, true, false>(tq, tg, gin, qin, Q, N, D, 1, p, nullptr, nullptr, out_scores, eps,
+                                nullptr, st);
 }
 
 // dense [Q,N] cosine scores with both inverse norms supplied (a block of the large-k path)
@@ -773,7 +810,7 @@ irr_status bf16_scores_block(const void* q, const void* g, const float* g_inv_no
   if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   return launch<4, true, false>(tq, tg, g_inv_norm, q_inv_norm, Q, N, D, 1, p, nullptr, nullptr,
-                                out_scores, eps, st);
+                                out_scores, eps, nullptr, st);
 }
 
 }  // namespace irr

@@ -306,6 +306,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// monotone float <-> uint32 map (larger float -> larger unsigned); 0 is below every float
+__device__ __forceinline__ uint32_t orderable(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
 // ---- per-thread sorted top-k list in registers -----------------------------------------------
 // "better" = larger score, ties -> lower index (the rule irr_b200.h promises)
 __device__ __forceinline__ bool cand_better(float va, long long ia, float vb, long long ib) {
@@ -336,6 +345,24 @@ struct TopKList {
         }
       }
     }
+  }
+  // Same insert as push_ordered without a serial bubble chain: rank the candidate against all
+  // entries at once (independent compares), then every slot picks {keep, take from above, take the
+  // candidate} — high ILP, which matters with a single epilogue warp per scheduler.  `take` must
+  // imply s > v[KMAX-1]; lanes with take == false leave their list untouched.
+  __device__ __forceinline__ void insert_ranked(bool take, float s, IdxT idx) {
+    int c = 0;  // entries that stay ahead of s: the earlier (lower) index wins ties
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) c += (v[j] >= s) ? 1 : 0;
+    if (!take) c = KMAX;
+#pragma unroll
+    for (int j = KMAX - 1; j > 0; --j) {
+      const bool from_above = j > c;
+      const bool here = j == c;
+      v[j] = from_above ? v[j - 1] : (here ? s : v[j]);
+      i[j] = from_above ? i[j - 1] : (here ? idx : i[j]);
+    }
+    if (c == 0) { v[0] = s; i[0] = idx; }
   }
   // candidates in arbitrary order: full (score, index) comparison; idx < 0 = padding
   __device__ __forceinline__ void push_any(float s, IdxT idx) {

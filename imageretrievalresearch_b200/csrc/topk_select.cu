@@ -23,13 +23,6 @@ constexpr int SEL_KEYS = 1024;                // best + candidate buffer, power 
 constexpr int SEL_CHUNK = 2 * SEL_THREADS;    // columns scanned between flush checks
 constexpr int SEL_FLUSH_AT = SEL_KEYS - SEL_BEST - SEL_CHUNK;  // 256: buffer can take one more chunk
 
-__device__ __forceinline__ uint32_t orderable(float v) {
-  const uint32_t b = __float_as_uint(v);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float from_orderable(uint32_t o) {
-  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
-}
 __device__ __forceinline__ unsigned long long make_key(float v, uint32_t idx) {
   return (static_cast<unsigned long long>(orderable(v)) << 32) | (0xffffffffu - idx);
 }
