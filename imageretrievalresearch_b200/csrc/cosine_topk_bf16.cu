@@ -125,15 +125,23 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, i
         for (int j = 0; j < 32; ++j)
           if (c + j >= n_valid) v[j] = kNegInf;
       }
-      float mx = kNegInf;
+      // Which of the 32 columns does ANY row of this warp still want?  Every lane builds its own
+      // 32-bit take-mask with independent compares (no per-column vote/branch latency chain — there
+      // is a single epilogue warp per scheduler), one REDUX ORs the masks, and the insert code runs
+      // only for the set bits, which are rare once the thresholds are warm.
+      const float kth = top.v[KMAX - 1];
+      uint32_t mine = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
-      // warp-uniform skips: first the whole 32-column group, then each column
-      if (__any_sync(0xffffffffu, mx > top.v[KMAX - 1] && mx >= floor)) {
+      for (int j = 0; j < 32; ++j) mine |= ((v[j] > kth && v[j] >= floor) ? 1u : 0u) << j;
+      const uint32_t any = __reduce_or_sync(0xffffffffu, mine);
+      if (any) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const bool take = v[j] > top.v[KMAX - 1] && v[j] >= floor;
-          if (__any_sync(0xffffffffu, take)) top.insert_ranked(take, v[j], n0 + c + j);
+          if (any & (1u << j)) {  // warp-uniform
+            // re-evaluated: an insert earlier in this group may have raised this row's threshold
+            const bool take = v[j] > top.v[KMAX - 1] && v[j] >= floor;
+            top.insert_ranked(take, v[j], n0 + c + j);
+          }
         }
       }
     }
