@@ -93,6 +93,20 @@ Plan make_plan(int64_t Q, int64_t N) {
 // One accumulator tile (this thread = one query row, 256 gallery columns): TMEM -> registers 32
 // columns at a time, scale by the inverse gallery norms, and fold into the row's running top-k.
 // Columns arrive in increasing gallery index, so the strict '>' insert keeps the lower index on ties.
+// v[j] for a runtime (warp-uniform) j without spilling the array to local memory
+__device__ __forceinline__ float pick32(const float (&v)[32], int j) {
+  float a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+  return (j & 16) ? d[1] : d[0];
+}
+
 // `floor` is a lower bound on this row's final k-th best score published by other gallery chunks
 // (row_floor[], see below): anything strictly below it can be dropped without looking at the list.
 template <int KMAX, bool WRITE_SCORES>
@@ -134,15 +148,18 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, i
 #pragma unroll
       for (int j = 0; j < 32; ++j) mine |= ((v[j] > kth && v[j] >= floor) ? 1u : 0u) << j;
       const uint32_t any = __reduce_or_sync(0xffffffffu, mine);
-      if (any) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (any & (1u << j)) {  // warp-uniform
-            // re-evaluated: an insert earlier in this group may have raised this row's threshold
-            const bool take = v[j] > top.v[KMAX - 1] && v[j] >= floor;
-            top.insert_ranked(take, v[j], n0 + c + j);
-          }
-        }
+      // ONE copy of the insert code (it is ~120 instructions for KMAX=16; unrolled per column it
+      // would not fit the instruction cache): walk the set bits, fetching column j's score from
+      // the register array with a 5-level select tree on the warp-uniform j.
+      uint32_t todo = any;
+#pragma unroll 1
+      while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float sj = pick32(v, j);
+        // re-evaluated: an insert earlier in this group may have raised this row's threshold
+        const bool take = sj > top.v[KMAX - 1] && sj >= floor;
+        top.insert_ranked(take, sj, n0 + c + j);
       }
     }
   }
