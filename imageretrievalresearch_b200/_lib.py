@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libirr_b200.so"
 
-IRR_F32, IRR_BF16 = 0, 1
+IRR_F32, IRR_BF16, IRR_F16 = 0, 1, 2
 IRR_MAX_K = 256
 IRR_MAX_K_FUSED = 16
 IRR_ROW_STATS = 8
@@ -46,6 +46,11 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _f32, _vp, _sz, _vp]),
     "irr_pair_loss_bwd": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _i32,
                                  _vp, _vp, _vp]),
+    "irr_avgpool_fwd": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp]),
+    "irr_avgpool_bwd": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp]),
+    "irr_ce_pair_workspace_bytes": (_sz, [_i64]),
+    "irr_ce_pair_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp, _sz, _vp]),
+    "irr_ce_pair_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -29,6 +29,7 @@ SOURCES = [
     "cosine_topk_f32.cu",
     "cosine_topk_bf16.cu",
     "triplet_loss.cu",
+    "producer_consumer.cu",
 ]
 
 NVCC_FLAGS = [

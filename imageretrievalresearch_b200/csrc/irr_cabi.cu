@@ -47,6 +47,8 @@ void profile_mark_stop(cudaStream_t st) {
 
 namespace {
 
+bool any_float(irr_dtype dt) { return dt == IRR_F32 || dt == IRR_BF16 || dt == IRR_F16; }
+
 irr_status check_rows(const void* p, int32_t D, irr_dtype dt) {
   if (dt != IRR_F32 && dt != IRR_BF16) return IRR_ERR_UNSUPPORTED_DTYPE;
   if (D <= 0) return IRR_ERR_INVALID_ARG;
@@ -344,6 +346,41 @@ irr_status irr_pair_loss_bwd(const void* a_, const void* b_, const float* label,
   a.row_stats = const_cast<float*>(row_stats);
   a.dq = da; a.dp = db;
   return loss_bwd(a, grad_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_avgpool_fwd(const void* fm, irr_dtype in_dt, int64_t rows, int32_t hw, void* out,
+                           irr_dtype out_dt, irr_stream_t stream) {
+  if (rows < 0 || hw < 1 || (rows > 0 && (!fm || !out))) return IRR_ERR_INVALID_ARG;
+  if (!any_float(in_dt) || (out_dt != IRR_F32 && out_dt != IRR_BF16)) return IRR_ERR_UNSUPPORTED_DTYPE;
+  return avgpool_fwd(fm, in_dt, rows, hw, out, out_dt, reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_avgpool_bwd(const void* grad_out, irr_dtype go_dt, int64_t rows, int32_t hw,
+                           void* grad_fm, irr_dtype gf_dt, irr_stream_t stream) {
+  if (rows < 0 || hw < 1 || (rows > 0 && (!grad_out || !grad_fm))) return IRR_ERR_INVALID_ARG;
+  if ((go_dt != IRR_F32 && go_dt != IRR_BF16) || !any_float(gf_dt)) return IRR_ERR_UNSUPPORTED_DTYPE;
+  return avgpool_bwd(grad_out, go_dt, rows, hw, grad_fm, gf_dt, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t irr_ce_pair_workspace_bytes(int64_t B) { return B < 0 ? 0 : ce_pair_workspace_bytes(B); }
+
+irr_status irr_ce_pair_fwd(const void* a, const void* b, const int64_t* target, int64_t B, int32_t C,
+                           irr_dtype dt, int64_t ignore_index, float* out_loss, void* workspace,
+                           size_t workspace_bytes, irr_stream_t stream) {
+  if (B <= 0 || C < 1 || !a || !b || !target || !out_loss || !workspace) return IRR_ERR_INVALID_ARG;
+  if (!any_float(dt)) return IRR_ERR_UNSUPPORTED_DTYPE;
+  return ce_pair_fwd(a, b, target, B, C, dt, ignore_index, out_loss, workspace, workspace_bytes,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_ce_pair_bwd(const void* a, const void* b, const int64_t* target, int64_t B, int32_t C,
+                           irr_dtype dt, int64_t ignore_index, const float* grad_out,
+                           const void* workspace, void* da, void* db, irr_stream_t stream) {
+  if (B <= 0 || C < 1 || !a || !b || !target || !grad_out || !workspace || !da || !db)
+    return IRR_ERR_INVALID_ARG;
+  if (!any_float(dt)) return IRR_ERR_UNSUPPORTED_DTYPE;
+  return ce_pair_bwd(a, b, target, B, C, dt, ignore_index, grad_out, workspace, da, db,
+                     reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -70,6 +70,19 @@ irr_status f32_cosine_scores(const void* q, const void* g, const float* g_inv_no
                              const float* q_inv_norm, int64_t Q, int64_t N, int32_t D,
                              float* out_scores, cudaStream_t st);
 
+// producer_consumer.cu
+irr_status avgpool_fwd(const void* fm, int in_dt, int64_t rows, int32_t hw, void* out, int out_dt,
+                       cudaStream_t st);
+irr_status avgpool_bwd(const void* grad_out, int go_dt, int64_t rows, int32_t hw, void* grad_fm,
+                       int gf_dt, cudaStream_t st);
+size_t ce_pair_workspace_bytes(int64_t B);
+irr_status ce_pair_fwd(const void* a, const void* b, const int64_t* target, int64_t B, int32_t C,
+                       int dt, int64_t ignore_index, float* out_loss, void* ws, size_t ws_bytes,
+                       cudaStream_t st);
+irr_status ce_pair_bwd(const void* a, const void* b, const int64_t* target, int64_t B, int32_t C,
+                       int dt, int64_t ignore_index, const float* grad_out, const void* ws, void* da,
+                       void* db, cudaStream_t st);
+
 // triplet_loss.cu
 struct LossArgs {
   const void *q, *p, *n;       // n == nullptr: pair form (a = q, b = p)

@@ -54,7 +54,8 @@ enum {
   IRR_ERR_ROW_TOO_LONG = -7        /* D too large for the shared-memory staged loss kernels */
 };
 
-typedef enum { IRR_F32 = 0, IRR_BF16 = 1 } irr_dtype;
+/* IRR_F16 is accepted only where stated (feature maps and logits produced under fp16 autocast) */
+typedef enum { IRR_F32 = 0, IRR_BF16 = 1, IRR_F16 = 2 } irr_dtype;
 
 /* largest k of irr_cosine_topk; up to IRR_MAX_K_FUSED the register-resident epilogues select inside
  * the GEMM kernel (scores never written), above it a dense score block of bounded size is
@@ -225,6 +226,37 @@ IRR_API irr_status irr_pair_loss_bwd(const void* a, const void* b, const float* 
                                      const float* grad_out, int64_t B, int32_t D, irr_dtype dt,
                                      int32_t kind, float margin, int32_t reduce_mean, void* da,
                                      void* db, irr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Producer / consumer steps next to the path
+ *
+ * get_fm — global average pool, replaces
+ *     pool = AvgPool2d((fm.shape[2], fm.shape[3])); torch.reshape(pool(fm), (-1, fm.shape[1]))
+ *   train/train_efficient_cos_con_ce_loss.py:103-122
+ * fm: contiguous [rows = B*C, hw = H*W] of in_dt (F32 / BF16 / F16); out: [rows] of out_dt
+ * (F32 / BF16) = mean over hw, i.e. the [B,C] embedding rows the path consumes.
+ * Backward: grad_fm[r, :] = grad_out[r] / hw.
+ * ------------------------------------------------------------------------------------------ */
+IRR_API irr_status irr_avgpool_fwd(const void* fm, irr_dtype in_dt, int64_t rows, int32_t hw,
+                                   void* out, irr_dtype out_dt, irr_stream_t stream);
+IRR_API irr_status irr_avgpool_bwd(const void* grad_out, irr_dtype go_dt, int64_t rows, int32_t hw,
+                                   void* grad_fm, irr_dtype gf_dt, irr_stream_t stream);
+
+/* Cross-entropy of two logits tensors against one target vector, replaces
+ *     loss_ce = CrossEntropyLoss()(lbl_ims, clss) + CrossEntropyLoss()(lbl_poss, clss)
+ *   train/train_efficient_cos_con_ce_loss.py:160,240-242
+ * a, b: [B,C] logits of dt (F32 / BF16 / F16); target int64[B] (ignore_index rows are skipped,
+ * 'mean' divides by the number of kept rows).  out_loss: device fp32[3] = {sum, ce(a), ce(b)}.
+ * The forward leaves what the backward needs in `workspace` (irr_ce_pair_workspace_bytes);
+ * backward: grad_out = device fp32[1] upstream gradient of out_loss[0]; da / db [B,C] of dt. */
+IRR_API size_t irr_ce_pair_workspace_bytes(int64_t B);
+IRR_API irr_status irr_ce_pair_fwd(const void* a, const void* b, const int64_t* target, int64_t B,
+                                   int32_t C, irr_dtype dt, int64_t ignore_index, float* out_loss,
+                                   void* workspace, size_t workspace_bytes, irr_stream_t stream);
+IRR_API irr_status irr_ce_pair_bwd(const void* a, const void* b, const int64_t* target, int64_t B,
+                                   int32_t C, irr_dtype dt, int64_t ignore_index,
+                                   const float* grad_out, const void* workspace, void* da, void* db,
+                                   irr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -135,6 +135,29 @@ def golden_retrieval():
     return out
 
 
+def golden_producer_consumer():
+    """get_fm (:103-122) and loss_ce (:160,240-242) exactly as the reference calls them."""
+    out = {}
+    g = torch.Generator().manual_seed(61)
+    fm = torch.randn(5, 37, 7, 7, generator=g).requires_grad_(True)
+    pool = torch.nn.AvgPool2d((fm.shape[2], fm.shape[3]))
+    emb = torch.reshape(pool(fm), (-1, fm.shape[1]))
+    up = torch.randn(5, 37, generator=g)
+    (emb * up).sum().backward()
+    out.update(pool_fm=fm.detach().numpy(), pool_out=emb.detach().numpy(), pool_up=up.numpy(),
+               pool_grad=fm.grad.numpy())
+    la = torch.randn(19, 125, generator=g).mul(3).requires_grad_(True)
+    lb = torch.randn(19, 125, generator=g).mul(3).requires_grad_(True)
+    clss = torch.randint(0, 125, (19,), generator=g)
+    ce_loss = torch.nn.CrossEntropyLoss()                               # reference :160
+    l_ims, l_poss = ce_loss(la, clss), ce_loss(lb, clss)                # :240-241
+    (1.7 * (l_ims + l_poss)).backward()                                 # :242 (+ an upstream scale)
+    out.update(ce_a=la.detach().numpy(), ce_b=lb.detach().numpy(), ce_t=clss.numpy(),
+               ce_losses=np.array([(l_ims + l_poss).item(), l_ims.item(), l_poss.item()], dtype=np.float32),
+               ce_da=la.grad.numpy(), ce_db=lb.grad.numpy())
+    return out
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
@@ -142,6 +165,7 @@ def main():
     ContrastiveLoss = load_reference_contrastive()
     np.savez_compressed(OUT / "losses.npz", **golden_losses(ContrastiveLoss))
     np.savez_compressed(OUT / "retrieval.npz", **golden_retrieval())
+    np.savez_compressed(OUT / "producer_consumer.npz", **golden_producer_consumer())
     for f in sorted(OUT.glob("*.npz")):
         print(f, f.stat().st_size, "bytes")
 

@@ -243,6 +243,24 @@ def four_losses_and_grads(q, p, n, margin: float, weights=(1.0, 1.0, 1.0, 1.0),
 
 
 # -------------------------------------------------------------------------------------------------
+# a8 / next rows: the producer (get_fm) and the consumer (cross-entropy) either side of the path
+# -------------------------------------------------------------------------------------------------
+def get_fm(fm: torch.Tensor) -> torch.Tensor:
+    """train/train_efficient_cos_con_ce_loss.py:103-122, verbatim."""
+    pool = torch.nn.AvgPool2d((fm.shape[2], fm.shape[3]))                               # :120
+    return torch.reshape(pool(fm), (-1, fm.shape[1]))                                   # :122
+
+
+def loss_ce(lbl_ims: torch.Tensor, lbl_poss: torch.Tensor, clss: torch.Tensor):
+    """train/train_efficient_cos_con_ce_loss.py:160,240-242: CrossEntropyLoss() on the query and
+    positive logits, summed.  Returns (loss_ce, loss_ce_ims, loss_ce_poss)."""
+    ce_loss = torch.nn.CrossEntropyLoss()                                               # :160
+    loss_ce_ims = ce_loss(lbl_ims, clss)                                                # :240
+    loss_ce_poss = ce_loss(lbl_poss, clss)                                              # :241
+    return loss_ce_ims + loss_ce_poss, loss_ce_ims, loss_ce_poss                        # :242
+
+
+# -------------------------------------------------------------------------------------------------
 # K3  candidate merge (new in the sharded design; oracle = sort by (score desc, index asc))
 # -------------------------------------------------------------------------------------------------
 def merge_candidates(cand_val: torch.Tensor, cand_idx: torch.Tensor, k: int

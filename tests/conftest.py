@@ -42,3 +42,9 @@ def golden_losses():
 def golden_retrieval():
     import numpy as np
     return dict(np.load(GOLDEN / "retrieval.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_pc():
+    import numpy as np
+    return dict(np.load(GOLDEN / "producer_consumer.npz"))

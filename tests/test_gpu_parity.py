@@ -514,3 +514,95 @@ def test_dedup_edge_cases():
     assert torch.equal(d.labels.cpu(), wl) and torch.equal(d.indices.cpu(), wi)
     d1 = irr.class_dedup_topk(irr.TopK(val.cuda(), idx.cuda()), lab.cuda(), 1)
     assert d1.labels.flatten().tolist() == [7, 2, 1] and d1.hits is None
+
+
+# -------------------------------------------------------------------------------------------------
+# next rows: get_fm producer and cross-entropy consumer
+# -------------------------------------------------------------------------------------------------
+def test_golden_get_fm_and_ce(golden_pc):
+    g = golden_pc
+    fm = T(g["pool_fm"]).requires_grad_(True)
+    emb = irr.get_fm(fm)
+    assert emb.shape == (5, 37) and (emb - T(g["pool_out"])).abs().max() < 1e-6
+    (emb * T(g["pool_up"])).sum().backward()
+    assert (fm.grad - T(g["pool_grad"])).abs().max() < 1e-7
+    a, b = T(g["ce_a"]).requires_grad_(True), T(g["ce_b"]).requires_grad_(True)
+    ce = irr.cross_entropy_pair(a, b, T(g["ce_t"]))
+    want = T(g["ce_losses"])
+    got = torch.stack([ce.loss.detach(), ce.loss_a, ce.loss_b])
+    assert ((got - want).abs() <= LOSS_REL * want.abs()).all(), (got, want)
+    (1.7 * ce.loss).backward()
+    assert rel(a.grad, T(g["ce_da"])) < GRAD_REL and rel(b.grad, T(g["ce_db"])) < GRAD_REL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,C,H,W", [(64, 1536, 7, 7), (3, 130, 5, 3), (2, 1920, 8, 8), (1, 5, 1, 1),
+                                     (7, 200, 32, 32)])
+def test_get_fm_shapes(dtype, B, C, H, W):
+    torch.manual_seed(B * C)
+    fm = torch.randn(B, C, H, W).to(dtype)
+    want = ref.get_fm(fm.float())
+    for out_dtype in (torch.float32, torch.bfloat16):
+        got = irr.get_fm(fm.cuda(), out_dtype=out_dtype)
+        assert got.dtype == out_dtype and got.shape == (B, C)
+        tol = 1e-6 if out_dtype == torch.float32 else 8e-3
+        assert (got.float().cpu() - want).abs().max() <= tol * max(1.0, want.abs().max().item())
+    x = fm.cuda().requires_grad_(True)
+    up = torch.randn(B, C, device="cuda")
+    (irr.get_fm(x).float() * up).sum().backward()
+    want_g = (up / (H * W))[:, :, None, None].expand(B, C, H, W)
+    assert x.grad.dtype == dtype
+    assert (x.grad.float() - want_g).abs().max() <= (1e-7 if dtype == torch.float32 else 4e-3)
+    # channels_last feature maps (what cuDNN backbones often produce)
+    cl = fm.cuda().contiguous(memory_format=torch.channels_last)
+    assert torch.equal(irr.get_fm(cl, out_dtype=torch.float32), irr.get_fm(fm.cuda(), out_dtype=torch.float32))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,C", [(64, 125), (4096, 1000), (1, 2), (33, 31)])
+def test_cross_entropy_pair(dtype, B, C):
+    torch.manual_seed(B + C)
+    a, b = (torch.randn(B, C) * 4).to(dtype), (torch.randn(B, C) * 4).to(dtype)
+    t = torch.randint(0, C, (B,))
+    if B > 3:
+        t[1] = -100                                     # ignore_index row
+    ar, br = a.float().requires_grad_(True), b.float().requires_grad_(True)
+    tot, la, lb = ref.loss_ce(ar, br, t)
+    tot.backward()
+    ac, bc = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    ce = irr.cross_entropy_pair(ac, bc, t.cuda())
+    ce.loss.backward()
+    got = torch.stack([ce.loss.detach(), ce.loss_a, ce.loss_b]).cpu()
+    want = torch.stack([tot, la, lb]).detach()
+    assert ((got - want).abs() <= LOSS_REL * want.abs() + 1e-7).all(), (got, want)
+    gtol = GRAD_REL if dtype == torch.float32 else 1e-2
+    assert rel(ac.grad.float().cpu(), ar.grad) < gtol and rel(bc.grad.float().cpu(), br.grad) < gtol
+    assert ac.grad.dtype == dtype
+
+
+def test_training_step_composition():
+    """training_step's loss = loss_cos + loss_con + loss_ce (:245) end to end through the drop-ins,
+    starting from [B,C,7,7] feature maps, against the oracle."""
+    torch.manual_seed(5)
+    B, C, ncls = 32, 256, 20
+    fms = [torch.randn(B, C, 7, 7) + 0.5 for _ in range(3)]
+    Wc = torch.randn(ncls, C) * 0.05
+    clss = torch.randint(0, ncls, (B,))
+    # oracle
+    fr = [f.clone().requires_grad_(True) for f in fms]
+    eq, ep, en = [ref.get_fm(f) for f in fr]
+    l4 = ref.four_losses(eq, ep, en, 0.3)
+    lce, _, _ = ref.loss_ce(eq @ Wc.T, ep @ Wc.T, clss)
+    want = l4.sum() + lce
+    want.backward()
+    # B200 path
+    fc = [f.cuda().requires_grad_(True) for f in fms]
+    gq, gp, gn = [irr.get_fm(f) for f in fc]
+    tl = irr.triplet_losses(gq, gp, gn, 0.3)
+    Wd = Wc.cuda()
+    ce = irr.cross_entropy_pair(gq @ Wd.T, gp @ Wd.T, clss.cuda())
+    got = tl.loss_cos + tl.loss_con + ce.loss
+    got.backward()
+    assert abs(got.item() - want.item()) <= LOSS_REL * abs(want.item())
+    for a, b in zip(fc, fr):
+        assert rel(a.grad.cpu(), b.grad) < GRAD_REL

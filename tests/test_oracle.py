@@ -159,3 +159,18 @@ def test_notebook_class_dedup_matches_reference(golden_retrieval):
     lab, ind, val = ref.class_dedup_from_ranked(si, sv.float(), cls, 3)
     assert torch.equal(lab, T(g["nb_r"])) and torch.equal(ind, T(g["nb_i"]))
     assert (val - T(g["nb_v"])).abs().max() < 3e-7
+
+
+def test_get_fm_and_loss_ce_match_reference(golden_pc):
+    g = golden_pc
+    fm = T(g["pool_fm"]).requires_grad_(True)
+    emb = ref.get_fm(fm)
+    assert torch.equal(emb.detach(), T(g["pool_out"]))
+    (emb * T(g["pool_up"])).sum().backward()
+    assert torch.equal(fm.grad, T(g["pool_grad"]))
+    a, b = T(g["ce_a"]).requires_grad_(True), T(g["ce_b"]).requires_grad_(True)
+    tot, la, lb = ref.loss_ce(a, b, T(g["ce_t"]))
+    assert torch.allclose(torch.stack([tot, la, lb]).detach(), T(g["ce_losses"]), rtol=1e-6)
+    (1.7 * tot).backward()
+    assert torch.allclose(a.grad, T(g["ce_da"]), rtol=1e-6, atol=1e-9)
+    assert torch.allclose(b.grad, T(g["ce_db"]), rtol=1e-6, atol=1e-9)
