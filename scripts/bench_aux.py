@@ -158,6 +158,30 @@ def notebook():
         print(json.dumps({"what": "same size, fused k=3 path", "dtype": str(dt), "ms": ms3}), flush=True)
 
 
+def losses_big():
+    """The loss kernel away from launch/ramp effects: 64k triplets (2.4 GB of traffic per launch)."""
+    B, D = 65536, 1536
+    q, p_, n = [torch.randn(B, D, device="cuda") for _ in range(3)]
+    ms = graphed(lambda i: irr.triplet_losses_fwd_bwd(q, p_, n, 0.3), 4)
+    by = 6 * B * D * 4
+    print(json.dumps({"what": "fused triplet losses fwd+bwd", "B": B, "D": D, "dtype": "torch.float32",
+                      "us": ms * 1e3, "GBps": by / ms / 1e6, "hbm_frac": by / ms / 1e6 / PEAKS["hbm_gbs"]}),
+          flush=True)
+
+
+def pool():
+    """get_fm (global average pool) and the CE pair at the training batch and at a large batch."""
+    for B in (64, 2048):
+        fm = torch.randn(B, 1536, 7, 7, device="cuda")
+        ms = graphed(lambda i: irr.get_fm(fm), 10)
+        by = fm.numel() * 4 + B * 1536 * 4
+        print(json.dumps({"what": "get_fm global average pool fwd", "shape": list(fm.shape), "us": ms * 1e3,
+                          "GBps": by / ms / 1e6, "hbm_frac": by / ms / 1e6 / PEAKS["hbm_gbs"]}), flush=True)
+        ms = timed(lambda i: torch.nn.functional.adaptive_avg_pool2d(fm, 1).reshape(B, 1536), 20)
+        print(json.dumps({"what": "torch AvgPool on the same GPU", "shape": list(fm.shape), "us": ms * 1e3}),
+              flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["losses", "f32", "smallq"]
     for w in which:
