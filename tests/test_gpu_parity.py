@@ -566,7 +566,7 @@ def test_cross_entropy_pair(dtype, B, C):
     t = torch.randint(0, C, (B,))
     if B > 3:
         t[1] = -100                                     # ignore_index row
-    ar, br = a.float().requires_grad_(True), b.float().requires_grad_(True)
+    ar, br = a.float().clone().requires_grad_(True), b.float().clone().requires_grad_(True)
     tot, la, lb = ref.loss_ce(ar, br, t)
     tot.backward()
     ac, bc = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
