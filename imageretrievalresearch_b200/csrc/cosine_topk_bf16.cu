@@ -4,9 +4,10 @@
 // loops (train/train_efficient_cos_con_ce_loss.py:270-281,374-392;
 // inference/training_analysis.ipynb:231-251) for all query rows in one launch.
 //
-// Layout / roles (one persistent CTA per SM, 384 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles of Q (128 x 64) and G (256 x 64),
-//               128-byte swizzle, into a 4-stage shared-memory ring (48 KB / stage)
+// Layout / roles of the single-CTA kernel (one persistent CTA per SM, 384 threads; the CTA-pair
+// kernel further down is the cta_group::2 variant for large batches):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles of Q (128 or 256 x 64) and G (256 x 64),
+//               128-byte swizzle, into a 4- or 3-stage shared-memory ring (48 / 64 KB per stage)
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256, K=16) x4 per stage,
 //               fp32 accumulators in TMEM, two accumulator stages (2 x 256 of the 512 columns)
 //   warp 2      TMEM allocator
@@ -33,12 +34,9 @@ constexpr int BLOCK_M = 128;   // query rows per tile  (UMMA M)
 constexpr int BLOCK_N = 256;   // gallery rows per tile (UMMA N)
 constexpr int BLOCK_K = 64;    // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
@@ -46,21 +44,17 @@ constexpr int NORM_WARP0 = 8;   // warps 8-11: gallery-norm warps of the fused-n
 constexpr int NORM_THREADS = 128;
 
 // dynamic shared memory carve-up (base aligned to 1024 B for the 128-byte swizzle)
-constexpr int SMEM_TILES = STAGES * STAGE_BYTES;                 // 196608
 constexpr int SMEM_GN = ACC_STAGES * BLOCK_N * 4;                // inverse gallery norms per tile
-constexpr int SMEM_BARS = (2 * STAGES + 3 * ACC_STAGES) * 8;
-constexpr int SMEM_TOTAL = SMEM_TILES + SMEM_GN + SMEM_BARS + 16;
-constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;                    // slack for manual alignment
 
 struct Plan {
   int m_tiles, n_tiles, tiles_per_chunk, n_chunks, grid;
 };
 
 // Chunk the gallery tiles so that (query tiles x chunks) spreads evenly over the SMs.
-Plan make_plan(int64_t Q, int64_t N) {
+Plan make_plan(int64_t Q, int64_t N, int MT = 1) {
   Plan p;
   const int sms = num_sms();
-  p.m_tiles = static_cast<int>((Q + BLOCK_M - 1) / BLOCK_M);
+  p.m_tiles = static_cast<int>((Q + MT * BLOCK_M - 1) / (MT * BLOCK_M));
   p.n_tiles = static_cast<int>((N + BLOCK_N - 1) / BLOCK_N);
   if (p.m_tiles < 1) p.m_tiles = 1;
   if (p.n_tiles < 1) p.n_tiles = 1;
@@ -182,11 +176,33 @@ __device__ __forceinline__ void publish_floor(uint32_t* row_floor, int row, int 
   if (row < Q && top.v[KMAX - 1] > floor) atomicMax(row_floor + row, orderable(top.v[KMAX - 1]));
 }
 
-// FUSE_NORM (single query tile: every gallery tile is consumed by exactly one CTA): four extra
-// warps square-sum the gallery rows out of the SAME shared-memory stages the MMA reads, so the
-// gallery crosses HBM once per search and no inverse-norm pre-pass exists.  With several query
-// tiles a gallery tile is consumed by many CTAs and the norms come from g_inv_norm instead.
-template <int KMAX, bool WRITE_SCORES, bool FUSE_NORM>
+// Geometry of the single-CTA kernel for MT query tiles (MT*128 rows) per work unit.
+//   MT = 1: 4 stages x (16 KB A + 32 KB B), two accumulator stages (2 x 256 TMEM columns)
+//   MT = 2: 3 stages x (32 KB A + 32 KB B), ONE accumulator stage holding both tiles (2 x 256
+//           columns): a gallery tile is staged once and multiplied against 256 query rows, so
+//           batches of 129..512 queries stream the gallery once per 256 queries instead of once per
+//           128.  That regime is HBM-bound, so the epilogue not overlapping the next tile's MMAs
+//           costs little (the TMA ring keeps filling meanwhile).
+template <int MT>
+struct SC {
+  static constexpr int STAGES = MT == 1 ? 4 : 3;
+  static constexpr int ACC = MT == 1 ? 2 : 1;
+  static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int A_BYTES = MT * A_TILE_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  static constexpr int TILES = STAGES * STAGE_BYTES;
+  static constexpr int GN = ACC * BLOCK_N * 4;
+  static constexpr int BARS = (2 * STAGES + 3 * ACC) * 8;
+  static constexpr int ALLOC = TILES + GN + BARS + 16 + 1024;
+  static_assert(MT * ACC * BLOCK_N <= TMEM_COLS, "accumulators exceed TMEM");
+  static_assert(TILES <= 196608, "stage ring exceeds the shared-memory budget");
+};
+
+// FUSE_NORM: four extra warps square-sum the gallery rows out of the SAME shared-memory stages the
+// MMA reads, so the gallery crosses HBM once per search and no inverse-norm pre-pass exists (used
+// when a gallery tile has one or two consumers; with many query tiles the norms come from
+// g_inv_norm instead).
+template <int KMAX, bool WRITE_SCORES, bool FUSE_NORM, int MT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         const __grid_constant__ CUtensorMap tmap_g,
@@ -195,20 +211,24 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         int tiles_per_chunk, int n_chunks, float* __restrict__ part_val,
                         int32_t* __restrict__ part_idx, float* __restrict__ scores_out,
                         uint64_t g_policy, float eps, int a_rows, uint32_t* __restrict__ row_floor) {
+  using G = SC<MT>;
+  constexpr int STAGES = G::STAGES;
+  constexpr int ACC = G::ACC;
+  constexpr int STAGE_BYTES = G::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const uint32_t bars = smem_base + SMEM_TILES + SMEM_GN;
+  const uint32_t bars = smem_base + G::TILES + G::GN;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC_STAGES + s); };
-  auto gnfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 * ACC_STAGES + s); };
-  const uint32_t tmem_slot = bars + SMEM_BARS;
-  float* gn_smem = reinterpret_cast<float*>(smem_gen + SMEM_TILES);
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC + s); };
+  auto gnfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 * ACC + s); };
+  const uint32_t tmem_slot = bars + G::BARS;
+  float* gn_smem = reinterpret_cast<float*>(smem_gen + G::TILES);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + SMEM_TILES + SMEM_GN + SMEM_BARS);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + G::TILES + G::GN + G::BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -224,7 +244,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // once each of the four norm warps has read it
       mbar_init(empty_bar(s), FUSE_NORM ? 1 + NORM_THREADS / 32 : 1);
     }
-    for (int s = 0; s < ACC_STAGES; ++s) {
+    for (int s = 0; s < ACC; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), EPI_THREADS / 32);
       mbar_init(gnfull_bar(s), NORM_THREADS / 32);
@@ -232,12 +252,12 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
-  if (a_rows < BLOCK_M) {
+  if (a_rows < MT * BLOCK_M) {
     // small query batch: the TMA box only covers the first a_rows rows of each A stage; the MMA
-    // still reads 128 rows, so the rest is zeroed once here (their accumulator rows are ignored)
+    // still reads MT*128 rows, so the rest is zeroed once here (their accumulator rows are ignored)
     for (int s = 0; s < STAGES; ++s) {
       uint4* a = reinterpret_cast<uint4*>(smem_gen + s * STAGE_BYTES);
-      for (int i = threadIdx.x; i < A_STAGE_BYTES / 16; i += NUM_THREADS)
+      for (int i = threadIdx.x; i < G::A_BYTES / 16; i += NUM_THREADS)
         a[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     fence_proxy_async_smem();  // generic-proxy zeros ordered before the async-proxy (TMA) writes
@@ -262,9 +282,9 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
           mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
           if (lane == 0) {
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-            const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+            const uint32_t b_dst = a_dst + G::A_BYTES;
             mbar_arrive_expect_tx(full_bar(stage), a_rows * (BLOCK_K * 2) + B_STAGE_BYTES);
-            tma_load_2d(a_dst, &tmap_q, kb * BLOCK_K, mt * BLOCK_M, full_bar(stage),
+            tma_load_2d(a_dst, &tmap_q, kb * BLOCK_K, mt * (MT * BLOCK_M), full_bar(stage),
                         kPolicyEvictLast);
             tma_load_2d(b_dst, &tmap_g, kb * BLOCK_K, t * BLOCK_N, full_bar(stage), g_policy);
           }
@@ -284,25 +304,28 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t0 = chunk * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
       for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        const uint32_t as = it % ACC, aphase = (it / ACC) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u, 200 + as);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + as * (MT * BLOCK_N);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, 300 + stage);
           tcgen05_fence_after();
           if (lane == 0) {
             const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
-            const uint64_t adesc = umma_desc_k128(a_addr);
-            const uint64_t bdesc = umma_desc_k128(a_addr + A_STAGE_BYTES);
+            const uint64_t bdesc = umma_desc_k128(a_addr + G::A_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-              // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-byte units
-              umma_bf16_ss(tmem_d, adesc + 2u * kk, bdesc + 2u * kk, idesc,
-                           (kb > 0 || kk > 0) ? 1u : 0u);
+            for (int m = 0; m < MT; ++m) {
+              const uint64_t adesc = umma_desc_k128(a_addr + m * G::A_TILE_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-byte units
+                umma_bf16_ss(tmem_d + m * BLOCK_N, adesc + 2u * kk, bdesc + 2u * kk, idesc,
+                             (kb > 0 || kk > 0) ? 1u : 0u);
+              }
             }
             umma_commit(empty_bar(stage));                 // frees the smem stage when MMAs finish
-            if (kb == num_kb - 1) umma_commit(tfull_bar(as));  // accumulator ready
+            if (kb == num_kb - 1) umma_commit(tfull_bar(as));  // accumulator(s) ready
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -329,7 +352,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
         float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, 600 + stage);
-          const uint8_t* b = smem_gen + stage * STAGE_BYTES + A_STAGE_BYTES;
+          const uint8_t* b = smem_gen + stage * STAGE_BYTES + G::A_BYTES;
           const uint4* r0 = reinterpret_cast<const uint4*>(b + nt * 128);
           const uint4* r1 = reinterpret_cast<const uint4*>(b + (nt + NORM_THREADS) * 128);
 #pragma unroll
@@ -354,8 +377,8 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (lane == 0) mbar_arrive(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
-        // the epilogue must be done with the norms it read two tiles ago from this buffer
+        const uint32_t as = it % ACC, aphase = (it / ACC) & 1u;
+        // the epilogue must be done with the norms it last read from this buffer
         mbar_wait(tempty_bar(as), aphase ^ 1u, 700 + as);
         float* gn = gn_smem + as * BLOCK_N;
         gn[nt] = 1.0f / fmaxf(sqrtf(s0a + s0b), eps);
@@ -370,18 +393,19 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
     const int row_in_tile = ew * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
-    TopKList<KMAX, int32_t> top;
+    TopKList<KMAX, int32_t> top[MT];
     uint32_t it = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int chunk = u / m_tiles, mt = u - chunk * m_tiles;
       const int t0 = chunk * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
-      const int row = mt * BLOCK_M + row_in_tile;
-      top.reset();
+      const int row0 = mt * (MT * BLOCK_M) + row_in_tile;   // this thread's row in query tile 0
+#pragma unroll
+      for (int m = 0; m < MT; ++m) top[m].reset();
       float qn = 1.0f;
-      if (WRITE_SCORES && row < Q) qn = q_inv_norm[row];
+      if (WRITE_SCORES && row0 < Q) qn = q_inv_norm[row0];
       for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        const uint32_t as = it % ACC, aphase = (it / ACC) & 1u;
         const int n0 = t * BLOCK_N;
         float* gn = gn_smem + as * BLOCK_N;
         if (FUSE_NORM) {
@@ -395,21 +419,31 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_wait(tfull_bar(as), aphase, 400 + as);
         tcgen05_fence_after();
         const int n_valid = min(BLOCK_N, N - n0);
-        const float floor = WRITE_SCORES ? kNegInf : read_floor(row_floor, row, Q);
-        epilogue_tile<KMAX, WRITE_SCORES>(tmem_base + lane_base + as * BLOCK_N, gn, n0, n_valid, row,
-                                          Q, N, qn, scores_out, top, floor);
-        if (!WRITE_SCORES) publish_floor<KMAX>(row_floor, row, Q, top, floor);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const int row = row0 + m * BLOCK_M;
+          const float floor = WRITE_SCORES ? kNegInf : read_floor(row_floor, row, Q);
+          epilogue_tile<KMAX, WRITE_SCORES>(tmem_base + lane_base + (as * MT + m) * BLOCK_N, gn, n0,
+                                            n_valid, row, Q, N, qn, scores_out, top[m], floor);
+          if (!WRITE_SCORES) publish_floor<KMAX>(row_floor, row, Q, top[m], floor);
+        }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
       }
-      if (!WRITE_SCORES && row < Q) {
-        const size_t o = (static_cast<size_t>(chunk) * Q + row) * k;
+      if (!WRITE_SCORES) {
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-          if (j < k) {
-            part_val[o + j] = top.v[j];
-            part_idx[o + j] = top.i[j];
+        for (int m = 0; m < MT; ++m) {
+          const int row = row0 + m * BLOCK_M;
+          if (row < Q) {
+            const size_t o = (static_cast<size_t>(chunk) * Q + row) * k;
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j) {
+              if (j < k) {
+                part_val[o + j] = top[m].v[j];
+                part_idx[o + j] = top[m].i[j];
+              }
+            }
           }
         }
       }
@@ -648,7 +682,7 @@ Plan make_plan_pair(int64_t Q, int64_t N) {
   return p;
 }
 
-// The pair kernel takes over in the tensor-bound regime (four or more query tiles; the HBM/tensor
+// The pair kernel takes over in the tensor-bound regime (more than four query tiles; the HBM/tensor
 // crossover is Q ~ 250).  Measured on B200 both kernels sit at the power-capped cuBLAS-sustained
 // level at Q=4096 (profiles/r01_notes.md); the pair kernel moves a third less data per flop.
 // IRR_NO_PAIR=1 / IRR_FORCE_PAIR=1 are measurement knobs for profiles/, not an API.
@@ -658,7 +692,7 @@ bool use_pair(int64_t Q) {
   if (no && no[0] == '1') return false;
   const char* force = getenv("IRR_FORCE_PAIR");
   if (force && force[0] == '1') return true;
-  return Q > 3 * BLOCK_M;
+  return Q > 4 * BLOCK_M;
 }
 
 template <int KMAX>
@@ -711,15 +745,19 @@ bool encode_bf16_rows(CUtensorMap* m, const void* base, int64_t rows, int64_t co
 
 // rows of the query TMA box: a whole 128-row tile, or for a single small batch just the rows
 // that exist (rounded up to the 8-row swizzle atom) — out-of-bounds rows cost TMA time
-int a_box_rows(int64_t Q) {
-  return Q >= BLOCK_M ? BLOCK_M : static_cast<int>((Q + 7) / 8 * 8);
+int a_box_rows(int64_t Q, int MT = 1) {
+  return Q >= MT * BLOCK_M ? MT * BLOCK_M : static_cast<int>((Q + 7) / 8 * 8);
 }
 
-template <int KMAX, bool WS, bool FN>
+// two query tiles per unit for batches of 129..512 queries (see SC<2>)
+int tiles_per_unit(int64_t Q) { return (Q > BLOCK_M && Q <= 4 * BLOCK_M) ? 2 : 1; }
+
+template <int KMAX, bool WS, bool FN, int MT = 1>
 irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, const float* qin,
                   int64_t Q, int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
                   float* scores, float eps, uint32_t* row_floor, cudaStream_t st) {
-  auto kern = cosine_topk_bf16_kernel<KMAX, WS, FN>;
+  auto kern = cosine_topk_bf16_kernel<KMAX, WS, FN, MT>;
+  constexpr int SMEM_ALLOC = SC<MT>::ALLOC;
   IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
   const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
   // a gallery streamed by a single query tile is read exactly once: do not let it displace the
@@ -729,7 +767,7 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
   kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(tq, tg, gin, qin, static_cast<int>(Q),
                                                 static_cast<int>(N), num_kb, k, p.m_tiles,
                                                 p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
-                                                scores, g_policy, eps, a_box_rows(Q), row_floor);
+                                                scores, g_policy, eps, a_box_rows(Q, MT), row_floor);
   if (!WS) profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -739,7 +777,7 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
 
 // workspace: [g_inv_norm fp32 N][part_val fp32 chunks*Q*k][part_idx i32 chunks*Q*k][row_floor u32 Q]
 size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
-  const Plan p = use_pair(Q) ? make_plan_pair(Q, N) : make_plan(Q, N);
+  const Plan p = use_pair(Q) ? make_plan_pair(Q, N) : make_plan(Q, N, tiles_per_unit(Q));
   const size_t parts = static_cast<size_t>(p.n_chunks) * Q * k;
   return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 +
          align_up(static_cast<size_t>(Q) * 4, 256) + 256;
@@ -753,7 +791,8 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   if (N > 0x7fffff00ll || Q > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
   if (ws_bytes < bf16_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
   const bool pair = use_pair(Q);
-  const Plan p = pair ? make_plan_pair(Q, N) : make_plan(Q, N);
+  const int mt = pair ? 1 : tiles_per_unit(Q);
+  const Plan p = pair ? make_plan_pair(Q, N) : make_plan(Q, N, mt);
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* gin_ws = reinterpret_cast<float*>(w);
   w += align_up(static_cast<size_t>(N) * 4, 256);
@@ -767,7 +806,8 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
 
   // single query tile and no cached norms: fuse the gallery norms into the tile stream;
   // otherwise the norms come from the caller's cache or from one streaming pre-pass
-  const bool fuse = !g_inv_norm && !pair && p.m_tiles == 1;
+  // fuse the gallery norms into the tile stream when a gallery tile has at most two consumers
+  const bool fuse = !g_inv_norm && !pair && p.m_tiles <= 2;
   const float* gin = g_inv_norm;
   if (!gin && !fuse) {
     irr_status s = row_inv_norms(g, N, D, IRR_BF16, eps, gin_ws, st);
@@ -775,7 +815,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
     gin = gin_ws;
   }
   CUtensorMap tq, tg;
-  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) ||
+  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q, mt)) ||
       !encode_bf16_rows(&tg, g, N, D, pair ? P_B_ROWS : BLOCK_N))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   irr_status s;
@@ -784,20 +824,19 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
       s = launch_pair<4>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, st);
     else
       s = launch_pair<16>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, st);
-  } else if (fuse) {
-    if (k <= 4)
-      s = launch<4, false, true>(tq, tg, nullptr, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps,
-                                 row_floor, st);
-    else
-      s = launch<16, false, true>(tq, tg, nullptr, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps,
-                                  row_floor, st);
   } else {
-    if (k <= 4)
-      s = launch<4, false, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps,
-                                  row_floor, st);
-    else
-      s = launch<16, false, false>(tq, tg, gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, eps,
-                                   row_floor, st);
+    // (KMAX, fused norms, query tiles per unit) -> instantiation
+#define IRR_LAUNCH_SC(KM, FN, MTV)                                                              \
+  s = launch<KM, false, FN, MTV>(tq, tg, FN ? nullptr : gin, nullptr, Q, N, D, k, p, pv, pi,    \
+                                 nullptr, eps, row_floor, st)
+    if (mt == 2) {
+      if (fuse) { if (k <= 4) IRR_LAUNCH_SC(4, true, 2); else IRR_LAUNCH_SC(16, true, 2); }
+      else      { if (k <= 4) IRR_LAUNCH_SC(4, false, 2); else IRR_LAUNCH_SC(16, false, 2); }
+    } else {
+      if (fuse) { if (k <= 4) IRR_LAUNCH_SC(4, true, 1); else IRR_LAUNCH_SC(16, true, 1); }
+      else      { if (k <= 4) IRR_LAUNCH_SC(4, false, 1); else IRR_LAUNCH_SC(16, false, 1); }
+    }
+#undef IRR_LAUNCH_SC
   }
   if (s != IRR_OK) return s;
   return merge_partials(pv, pi, p.n_chunks, Q, k, q, D, IRR_BF16, eps, idx_offset, out_val, out_idx,
