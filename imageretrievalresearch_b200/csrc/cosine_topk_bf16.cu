@@ -682,17 +682,19 @@ Plan make_plan_pair(int64_t Q, int64_t N) {
   return p;
 }
 
-// The pair kernel takes over in the tensor-bound regime (more than four query tiles; the HBM/tensor
-// crossover is Q ~ 250).  Measured on B200 both kernels sit at the power-capped cuBLAS-sustained
-// level at Q=4096 (profiles/r01_notes.md); the pair kernel moves a third less data per flop.
-// IRR_NO_PAIR=1 / IRR_FORCE_PAIR=1 are measurement knobs for profiles/, not an API.
-bool use_pair(int64_t Q) {
+// Which kernel serves a batch of Q queries (measured on B200 at N=1M, D=1536, see
+// profiles/r01_notes.md): the CTA-pair kernel for more than three query tiles (tensor-bound regime;
+// it moves a third less data per flop) and for 129..256 queries with cached norms (one pair streams
+// the gallery once); the single-CTA kernel otherwise.  IRR_NO_PAIR=1 / IRR_FORCE_PAIR=1 are
+// measurement knobs for profiles/, not an API.
+bool use_pair(int64_t Q, bool cached_norms) {
   if (Q <= BLOCK_M) return false;
   const char* no = getenv("IRR_NO_PAIR");
   if (no && no[0] == '1') return false;
   const char* force = getenv("IRR_FORCE_PAIR");
   if (force && force[0] == '1') return true;
-  return Q > 4 * BLOCK_M;
+  if (Q <= 2 * BLOCK_M) return cached_norms;
+  return Q > 3 * BLOCK_M;
 }
 
 template <int KMAX>
@@ -749,8 +751,12 @@ int a_box_rows(int64_t Q, int MT = 1) {
   return Q >= MT * BLOCK_M ? MT * BLOCK_M : static_cast<int>((Q + 7) / 8 * 8);
 }
 
-// two query tiles per unit for batches of 129..512 queries (see SC<2>)
-int tiles_per_unit(int64_t Q) { return (Q > BLOCK_M && Q <= 4 * BLOCK_M) ? 2 : 1; }
+// Two query tiles per unit (SC<2>) pay off where they remove the norm pre-pass: 129..256 queries
+// without cached norms (measured 0.81-0.89 ms vs 1.04-1.08 ms at N=1M; with cached norms the
+// CTA-pair kernel is faster there, and beyond 256 queries SC<2> is shared-memory-bandwidth bound).
+int tiles_per_unit(int64_t Q, bool cached_norms) {
+  return (!cached_norms && Q > BLOCK_M && Q <= 2 * BLOCK_M) ? 2 : 1;
+}
 
 template <int KMAX, bool WS, bool FN, int MT = 1>
 irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, const float* qin,
@@ -777,8 +783,14 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
 
 // workspace: [g_inv_norm fp32 N][part_val fp32 chunks*Q*k][part_idx i32 chunks*Q*k][row_floor u32 Q]
 size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
-  const Plan p = use_pair(Q) ? make_plan_pair(Q, N) : make_plan(Q, N, tiles_per_unit(Q));
-  const size_t parts = static_cast<size_t>(p.n_chunks) * Q * k;
+  // the caller may or may not pass cached norms: size for the larger of the two plans
+  size_t parts = 0;
+  for (int cached = 0; cached < 2; ++cached) {
+    const Plan p = use_pair(Q, cached) ? make_plan_pair(Q, N)
+                                       : make_plan(Q, N, tiles_per_unit(Q, cached));
+    const size_t n = static_cast<size_t>(p.n_chunks) * Q * k;
+    if (n > parts) parts = n;
+  }
   return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 +
          align_up(static_cast<size_t>(Q) * 4, 256) + 256;
 }
@@ -790,8 +802,9 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   if (device_cc() / 10 != 10) return IRR_ERR_UNSUPPORTED_DEVICE;
   if (N > 0x7fffff00ll || Q > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
   if (ws_bytes < bf16_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
-  const bool pair = use_pair(Q);
-  const int mt = pair ? 1 : tiles_per_unit(Q);
+  const bool cached = g_inv_norm != nullptr;
+  const bool pair = use_pair(Q, cached);
+  const int mt = pair ? 1 : tiles_per_unit(Q, cached);
   const Plan p = pair ? make_plan_pair(Q, N) : make_plan(Q, N, mt);
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* gin_ws = reinterpret_cast<float*>(w);
@@ -806,8 +819,8 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
 
   // single query tile and no cached norms: fuse the gallery norms into the tile stream;
   // otherwise the norms come from the caller's cache or from one streaming pre-pass
-  // fuse the gallery norms into the tile stream when a gallery tile has at most two consumers
-  const bool fuse = !g_inv_norm && !pair && p.m_tiles <= 2;
+  // fuse the gallery norms into the tile stream when every gallery tile has exactly one consumer
+  const bool fuse = !cached && !pair && p.m_tiles == 1;
   const float* gin = g_inv_norm;
   if (!gin && !fuse) {
     irr_status s = row_inv_norms(g, N, D, IRR_BF16, eps, gin_ws, st);
@@ -829,9 +842,8 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
 #define IRR_LAUNCH_SC(KM, FN, MTV)                                                              \
   s = launch<KM, false, FN, MTV>(tq, tg, FN ? nullptr : gin, nullptr, Q, N, D, k, p, pv, pi,    \
                                  nullptr, eps, row_floor, st)
-    if (mt == 2) {
-      if (fuse) { if (k <= 4) IRR_LAUNCH_SC(4, true, 2); else IRR_LAUNCH_SC(16, true, 2); }
-      else      { if (k <= 4) IRR_LAUNCH_SC(4, false, 2); else IRR_LAUNCH_SC(16, false, 2); }
+    if (mt == 2) {  // only chosen without cached norms: always the fused-norm variant
+      if (k <= 4) IRR_LAUNCH_SC(4, true, 2); else IRR_LAUNCH_SC(16, true, 2);
     } else {
       if (fuse) { if (k <= 4) IRR_LAUNCH_SC(4, true, 1); else IRR_LAUNCH_SC(16, true, 1); }
       else      { if (k <= 4) IRR_LAUNCH_SC(4, false, 1); else IRR_LAUNCH_SC(16, false, 1); }

@@ -291,10 +291,10 @@ def test_bf16_planted_100k():
     q32, gal32, _ = synthetic.planted_gallery(100_000, 1536, 300, 3, seed=3)
     lv = ref.cos_scores(q32, gal32).gather(1, pos)
     assert (res.values.cpu().double() - lv).abs().max() < BF16_ABS
-    # cached-norm gallery handle gives the same bits
+    # cached-norm gallery handle: same ranking, values equal up to the norm's summation order
     gal_h = irr.Gallery(gal.cuda())
     r2 = gal_h.search(q.cuda(), 3)
-    assert torch.equal(r2.indices, res.indices) and torch.equal(r2.values, res.values)
+    assert torch.equal(r2.indices, res.indices) and (r2.values - res.values).abs().max() < 1e-6
 
 
 def test_k10_bf16_d2560():
