@@ -10,9 +10,9 @@ from ._lib import IRR_MAX_K, IrrError, LIB_PATH, load as load_library
 from .losses import (ContrastiveLoss, CosineEmbeddingLoss, TripletFwdBwd, TripletLosses,
                      triplet_losses, triplet_losses_fwd_bwd)
 from .producer_consumer import CEPair, cross_entropy_pair, get_fm
-from .retrieval import (CosineSimilarity, DedupTopK, Gallery, TopK, class_dedup_topk, cosine_topk,
+from .retrieval import (CapturedSearch, CosineSimilarity, DedupTopK, Gallery, TopK, class_dedup_topk, cosine_topk,
                         top1_top3, top1_top3_dedup, topk_hits)
-from .sharded import ShardedGallery, exchange_candidates, shard_bounds
+from .sharded import PeerExchange, ShardedGallery, exchange_candidates, shard_bounds
 
 __all__ = [
     "IRR_MAX_K", "IrrError", "LIB_PATH", "load_library",
@@ -20,5 +20,5 @@ __all__ = [
     "triplet_losses", "triplet_losses_fwd_bwd",
     "CosineSimilarity", "Gallery", "TopK", "DedupTopK", "cosine_topk", "top1_top3", "topk_hits",
     "class_dedup_topk", "top1_top3_dedup", "get_fm", "cross_entropy_pair", "CEPair",
-    "ShardedGallery", "exchange_candidates", "shard_bounds",
+    "ShardedGallery", "PeerExchange", "CapturedSearch", "exchange_candidates", "shard_bounds",
 ]

@@ -16,6 +16,8 @@ IRR_MAX_K = 256
 IRR_MAX_K_FUSED = 16
 IRR_ROW_STATS = 8
 IRR_LOSS_COSINE_EMBEDDING, IRR_LOSS_CONTRASTIVE = 1, 2
+IRR_MAX_PEERS = 16
+IRR_XCHG_FUSED, IRR_XCHG_PUSH, IRR_XCHG_MERGE = 0, 1, 2
 
 _i32, _i64, _f32, _sz, _vp = C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_void_p
 
@@ -31,6 +33,15 @@ SIGNATURES = {
     "irr_row_inv_norms": (_i32, [_vp, _i64, _i32, _i32, _f32, _vp, _vp]),
     "irr_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "irr_topk_merge_strided": (_i32, [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "irr_topk_exchange_bytes": (_sz, [_i32, _i64, _i32]),
+    "irr_topk_exchange_merge": (_i32, [_vp, _vp, C.POINTER(_vp), _i32, _i32, _i64, _i32, _sz, _i32,
+                                       _vp, _vp, _vp]),
+    "irr_peer_export": (_i32, [_vp, _vp, C.POINTER(C.c_uint64)]),
+    "irr_peer_import": (_i32, [_vp, C.POINTER(_vp)]),
+    "irr_peer_close": (_i32, [_vp]),
+    "irr_cosine_topk_sharded_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
+    "irr_cosine_topk_sharded": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i64,
+                                       C.POINTER(_vp), _i32, _i32, _sz, _vp, _vp, _vp, _sz, _vp]),
     "irr_topk_hits": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _vp]),
     "irr_topk_class_dedup": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
                                     _vp]),

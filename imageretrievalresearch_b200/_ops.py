@@ -53,7 +53,11 @@ _zeroed: dict = {}
 
 
 def scratch(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Reusable uninitialised workspace for the current (device, stream)."""
+    """Reusable uninitialised workspace for the current (device, stream).  While a CUDA graph is
+    being captured the workspace comes from the graph's own memory pool instead (it must live and
+    die with the graph, not with this cache)."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -166,6 +170,35 @@ def topk_merge_packed(gathered: torch.Tensor, G: int, Q: int, k: int, idx_byte_o
                                          rank_bytes // 8, G, Q, k, ptr(vals), ptr(idx),
                                          stream_ptr(gathered.device)), "irr_topk_merge_strided")
     return vals, idx
+
+
+def topk_exchange_bytes(G: int, Q: int, k: int) -> int:
+    return int(_lib.load().irr_topk_exchange_bytes(G, Q, k))
+
+
+def topk_exchange_merge(vals: Optional[torch.Tensor], idx: Optional[torch.Tensor], peer_ptrs,
+                        rank: int, Q: int, k: int, buf_bytes: int, mode: int,
+                        device: torch.device,
+                        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                        ) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+    """irr_topk_exchange_merge: push this rank's [Q,k] lists into every rank's exchange buffer over
+    peer memory, wait for all G lists, merge (one kernel for k <= 16).  peer_ptrs: the G device
+    pointers of the exchange buffers as mapped into this process."""
+    lib = _lib.load()
+    G = len(peer_ptrs)
+    arr = (C.c_void_p * G)(*[int(p) for p in peer_ptrs])
+    ov = oi = None
+    if mode != _lib.IRR_XCHG_PUSH:
+        if out is None:
+            ov = torch.empty((Q, k), dtype=torch.float32, device=device)
+            oi = torch.empty((Q, k), dtype=torch.int64, device=device)
+        else:
+            ov, oi = out
+    with torch.cuda.device(device):
+        check(lib.irr_topk_exchange_merge(ptr(vals), ptr(idx), arr, G, rank, Q, k, buf_bytes, mode,
+                                          ptr(ov), ptr(oi), stream_ptr(device)),
+              "irr_topk_exchange_merge")
+    return None if ov is None else (ov, oi)
 
 
 def topk_hits(idx: torch.Tensor, q_label: Optional[torch.Tensor], g_label: Optional[torch.Tensor],

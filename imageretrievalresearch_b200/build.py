@@ -25,6 +25,7 @@ SOURCES = [
     "irr_cabi.cu",
     "row_norms.cu",
     "topk_merge.cu",
+    "topk_exchange.cu",
     "topk_select.cu",
     "cosine_topk_f32.cu",
     "cosine_topk_bf16.cu",

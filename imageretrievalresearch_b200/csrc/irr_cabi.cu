@@ -1,5 +1,7 @@
 // irr_cabi.cu — the extern "C" boundary declared in include/irr_b200.h: argument validation and
 // dispatch to the kernels.  Nothing here allocates, synchronises or falls back to the host.
+#include <string.h>
+
 #include "irr_common.cuh"
 #include "irr_kernels.h"
 
@@ -206,6 +208,88 @@ irr_status irr_topk_merge_strided(const float* cand_val, int64_t val_rank_stride
   if (k > IRR_MAX_K) return IRR_ERR_K_TOO_LARGE;
   return merge_candidates(cand_val, val_rank_stride, cand_idx, idx_rank_stride, G, Q, k, out_val,
                           out_idx, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t irr_topk_exchange_bytes(int32_t G, int64_t Q, int32_t k) {
+  if (G < 1 || G > IRR_MAX_PEERS || Q < 0 || k < 1 || k > IRR_MAX_K) return 0;
+  return topk_exchange_bytes(G, Q, k);
+}
+
+irr_status irr_topk_exchange_merge(const float* local_val, const int64_t* local_idx,
+                                   void* const* peer_bufs, int32_t G, int32_t rank, int64_t Q,
+                                   int32_t k, size_t buf_bytes, int32_t mode, float* out_val,
+                                   int64_t* out_idx, irr_stream_t stream) {
+  if (G < 1 || G > IRR_MAX_PEERS || rank < 0 || rank >= G || Q < 0 || k < 1 || !peer_bufs)
+    return IRR_ERR_INVALID_ARG;
+  if (k > IRR_MAX_K) return IRR_ERR_K_TOO_LARGE;
+  if (mode != IRR_XCHG_FUSED && mode != IRR_XCHG_PUSH && mode != IRR_XCHG_MERGE)
+    return IRR_ERR_INVALID_ARG;
+  if (mode != IRR_XCHG_MERGE && Q > 0 && (!local_val || !local_idx)) return IRR_ERR_INVALID_ARG;
+  if (mode != IRR_XCHG_PUSH && Q > 0 && (!out_val || !out_idx)) return IRR_ERR_INVALID_ARG;
+  return topk_exchange_merge(local_val, local_idx, peer_bufs, G, rank, Q, k, buf_bytes, mode,
+                             out_val, out_idx, reinterpret_cast<cudaStream_t>(stream));
+}
+
+irr_status irr_peer_export(const void* dev_ptr, uint8_t handle_out[64], uint64_t* offset_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+  if (!dev_ptr || !handle_out || !offset_out) return IRR_ERR_INVALID_ARG;
+  typedef int (*RangeFn)(unsigned long long*, size_t*, unsigned long long);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  IRR_CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return IRR_ERR_UNSUPPORTED_DEVICE;
+  unsigned long long base = 0;
+  size_t size = 0;
+  const unsigned long long p = reinterpret_cast<unsigned long long>(dev_ptr);
+  if (reinterpret_cast<RangeFn>(fn)(&base, &size, p) != 0 || base == 0 || p < base)
+    return IRR_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  IRR_CUDA_TRY(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  memcpy(handle_out, &h, 64);
+  *offset_out = p - base;
+  return IRR_OK;
+}
+
+irr_status irr_peer_import(const uint8_t handle[64], void** mapped_base) {
+  if (!handle || !mapped_base) return IRR_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  IRR_CUDA_TRY(cudaIpcOpenMemHandle(mapped_base, h, cudaIpcMemLazyEnablePeerAccess));
+  return IRR_OK;
+}
+
+irr_status irr_peer_close(void* mapped_base) {
+  if (!mapped_base) return IRR_ERR_INVALID_ARG;
+  IRR_CUDA_TRY(cudaIpcCloseMemHandle(mapped_base));
+  return IRR_OK;
+}
+
+size_t irr_cosine_topk_sharded_workspace_bytes(int64_t Q, int64_t N_local, int32_t D, int32_t k,
+                                               irr_dtype dt) {
+  const size_t inner = irr_cosine_topk_workspace_bytes(Q, N_local, D, k, dt);
+  if (inner == 0) return 0;
+  const size_t n = static_cast<size_t>(Q) * k;
+  return align_up(inner, 256) + align_up(n * 4, 256) + align_up(n * 8, 256);
+}
+
+irr_status irr_cosine_topk_sharded(const void* q, const void* g_local, const float* g_inv_norm,
+                                   int64_t Q, int64_t N_local, int32_t D, int32_t k, irr_dtype dt,
+                                   float eps, int64_t idx_offset, void* const* peer_bufs, int32_t G,
+                                   int32_t rank, size_t buf_bytes, float* out_val, int64_t* out_idx,
+                                   void* workspace, size_t workspace_bytes, irr_stream_t stream) {
+  if (Q < 0 || N_local < 0 || k < 1 || !workspace) return IRR_ERR_INVALID_ARG;
+  const size_t inner = irr_cosine_topk_workspace_bytes(Q, N_local, D, k, dt);
+  if (inner == 0 || workspace_bytes < irr_cosine_topk_sharded_workspace_bytes(Q, N_local, D, k, dt))
+    return IRR_ERR_WORKSPACE_TOO_SMALL;
+  uint8_t* w = static_cast<uint8_t*>(workspace) + align_up(inner, 256);
+  const size_t n = static_cast<size_t>(Q) * k;
+  float* lv = reinterpret_cast<float*>(w);
+  int64_t* li = reinterpret_cast<int64_t*>(w + align_up(n * 4, 256));
+  irr_status s = irr_cosine_topk(q, g_local, g_inv_norm, Q, N_local, D, k, dt, eps, idx_offset, lv,
+                                 li, workspace, inner, stream);
+  if (s != IRR_OK) return s;
+  return irr_topk_exchange_merge(lv, li, peer_bufs, G, rank, Q, k, buf_bytes, IRR_XCHG_FUSED,
+                                 out_val, out_idx, stream);
 }
 
 irr_status irr_topk_hits(const int64_t* idx, int64_t Q, int32_t k, const int64_t* q_label,

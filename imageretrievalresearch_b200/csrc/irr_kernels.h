@@ -33,6 +33,13 @@ irr_status topk_hits(const int64_t* idx, int64_t Q, int32_t k, const int64_t* q_
                      const int64_t* g_label, int64_t N, int64_t instance_offset, int64_t* out_hits,
                      cudaStream_t st);
 
+// topk_exchange.cu (peer-memory exchange fused with the cross-shard merge)
+size_t topk_exchange_bytes(int32_t G, int64_t Q, int32_t k);
+irr_status topk_exchange_merge(const float* local_val, const int64_t* local_idx,
+                               void* const* peer_bufs, int32_t G, int32_t rank, int64_t Q, int32_t k,
+                               size_t buf_bytes, int32_t mode, float* out_val, int64_t* out_idx,
+                               cudaStream_t st);
+
 // cosine_topk_bf16.cu (tcgen05 / TMA)
 size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k);
 irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
@@ -54,6 +61,10 @@ irr_status merge_candidates_large(const float* cand_val, int64_t val_rank_stride
                                   const int64_t* cand_idx, int64_t idx_rank_stride, int32_t G,
                                   int64_t Q, int32_t k, float* out_val, int64_t* out_idx,
                                   cudaStream_t st);
+irr_status merge_candidates_large_exchange(const uint8_t* buf, size_t state_off, size_t data_off,
+                                           size_t half_bytes, size_t slot_bytes, size_t idx_off,
+                                           int32_t G, int64_t Q, int32_t k, float* out_val,
+                                           int64_t* out_idx, cudaStream_t st);
 irr_status class_dedup(const float* val, const int64_t* idx, int64_t Q, int32_t k,
                        const int64_t* g_label, int64_t N, int32_t n_distinct, const int64_t* q_label,
                        int64_t* out_label, int64_t* out_idx, float* out_val, int64_t* out_hits,

@@ -101,9 +101,15 @@ __device__ __forceinline__ bool before(float va, long long ia, float vb, long lo
 __global__ void __launch_bounds__(SEL_THREADS)
 merge_large_kernel(const float* __restrict__ cand_val, int64_t val_rank_stride,
                    const int64_t* __restrict__ cand_idx, int64_t idx_rank_stride, int G, int64_t Q,
-                   int k, float* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+                   int k, float* __restrict__ out_val, int64_t* __restrict__ out_idx,
+                   const uint32_t* __restrict__ epoch_word, int64_t half_bytes) {
   __shared__ float sv[MRG_SLOTS];
   __shared__ long long si[MRG_SLOTS];
+  if (epoch_word && (__ldg(epoch_word) & 1u)) {
+    // lists sit in a peer-exchange buffer (topk_exchange.cu): odd epochs use the second half
+    cand_val = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(cand_val) + half_bytes);
+    cand_idx = reinterpret_cast<const int64_t*>(reinterpret_cast<const uint8_t*>(cand_idx) + half_bytes);
+  }
   const int64_t qi = blockIdx.x;
   const int total = G * k;
   for (int c = threadIdx.x; c < MRG_SLOTS; c += SEL_THREADS) {
@@ -215,7 +221,24 @@ irr_status merge_candidates_large(const float* cand_val, int64_t val_rank_stride
   if (static_cast<int64_t>(G) * k > MRG_SLOTS) return IRR_ERR_K_TOO_LARGE;
   if (Q == 0) return IRR_OK;
   merge_large_kernel<<<static_cast<unsigned>(Q), SEL_THREADS, 0, st>>>(
-      cand_val, val_rank_stride, cand_idx, idx_rank_stride, G, Q, k, out_val, out_idx);
+      cand_val, val_rank_stride, cand_idx, idx_rank_stride, G, Q, k, out_val, out_idx, nullptr, 0);
+  IRR_LAUNCH_CHECK();
+  return IRR_OK;
+}
+
+// the same merge reading the G lists in place from this rank's peer-exchange buffer; which of the
+// two halves holds them is decided on the device from the buffer's epoch word (topk_exchange.cu)
+irr_status merge_candidates_large_exchange(const uint8_t* buf, size_t state_off, size_t data_off,
+                                           size_t half_bytes, size_t slot_bytes, size_t idx_off,
+                                           int32_t G, int64_t Q, int32_t k, float* out_val,
+                                           int64_t* out_idx, cudaStream_t st) {
+  if (static_cast<int64_t>(G) * k > MRG_SLOTS) return IRR_ERR_K_TOO_LARGE;
+  if (Q == 0) return IRR_OK;
+  merge_large_kernel<<<static_cast<unsigned>(Q), SEL_THREADS, 0, st>>>(
+      reinterpret_cast<const float*>(buf + data_off), static_cast<int64_t>(slot_bytes / 4),
+      reinterpret_cast<const int64_t*>(buf + data_off + idx_off),
+      static_cast<int64_t>(slot_bytes / 8), G, Q, k, out_val, out_idx,
+      reinterpret_cast<const uint32_t*>(buf + state_off), static_cast<int64_t>(half_bytes));
   IRR_LAUNCH_CHECK();
   return IRR_OK;
 }

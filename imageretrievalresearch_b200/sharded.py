@@ -7,16 +7,26 @@ rank, over NCCL / NVLink on GPUs), and the merge kernel folds the ``[G,Q,k]`` ca
 resolve to the lower global index, which with contiguous shards equals the single-GPU answer.
 The reference has no sharded retrieval (its gallery is the rank-local batch,
 train/train_efficient_cos_con_ce_loss.py:385) — this is the scale-out of that same loop.
+
+Two transports carry the exchange step:
+  "peer"        (GPUs of one box) every rank's exchange buffer is mapped into all processes
+                (torch symmetric memory = CUDA VMM + handle exchange) and ONE kernel per rank stores
+                its lists into every peer over NVLink, publishes an epoch flag, waits for the G
+                lists and merges them (csrc/topk_exchange.cu) — no collective library on the path;
+  "collective"  one all-gather (NCCL on GPUs, gloo in the CPU tests) + the merge kernel.
+"auto" (default) takes "peer" when all ranks can map each other's memory and agrees on the
+answer across the group, so that no rank ever waits on a transport the others did not choose.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+import os
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
-from . import _ops
-from .retrieval import Gallery, TopK
+from . import _lib, _ops
+from .retrieval import CapturedSearch, Gallery, TopK
 
 
 def shard_bounds(total_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -67,15 +77,123 @@ def exchange_candidates(vals: torch.Tensor, idx: torch.Tensor,
     return unpack_candidates(out, G, Q, k)
 
 
+class PeerExchange:
+    """The G exchange buffers of a process group, one per rank, each mapped into every process.
+
+    Allocation and mapping are host plumbing; the protocol — remote stores, epoch flags, wait,
+    merge — is the kernel in csrc/topk_exchange.cu behind ``irr_topk_exchange_merge``.
+    mapping = "symm": torch symmetric memory (CUDA VMM allocation, handles passed between the
+    processes by torch);  mapping = "ipc": an ordinary torch allocation exported with CUDA IPC
+    (``irr_peer_export`` / ``irr_peer_import``), handles all-gathered over the process group.
+    All ranks must make the same sequence of calls on one stream.
+    """
+
+    def __init__(self, group: Optional[dist.ProcessGroup], device: torch.device, nbytes: int,
+                 mapping: str = "symm") -> None:
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > _lib.IRR_MAX_PEERS:
+            raise RuntimeError(f"peer exchange supports up to {_lib.IRR_MAX_PEERS} ranks")
+        self.device = device
+        self.nbytes = int(nbytes)
+        self.mapping = mapping
+        self._imported: List[int] = []
+        self.handle = None
+        if mapping == "symm":
+            import torch.distributed._symmetric_memory as symm_mem
+            self.buf = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=device)
+            self.handle = symm_mem.rendezvous(self.buf, self.group)
+            self.ptrs: List[int] = [int(p) for p in self.handle.buffer_ptrs]
+        elif mapping == "ipc":
+            self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+            self.ptrs = self._map_ipc()
+        else:
+            raise ValueError("mapping must be 'symm' or 'ipc'")
+        if len(self.ptrs) != self.world or self.ptrs[self.rank] != self.buf.data_ptr():
+            raise RuntimeError("peer mapping returned an unexpected pointer table")
+
+    def activate(self) -> None:
+        """Collective, called once every rank reported a successful mapping: flags / epoch start
+        at zero on every rank before anyone pushes."""
+        self.buf.zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+
+    def _map_ipc(self) -> List[int]:
+        import ctypes as C
+        lib = _lib.load()
+        handle = (C.c_uint8 * 64)()
+        off = C.c_uint64(0)
+        with torch.cuda.device(self.device):
+            st = lib.irr_peer_export(self.buf.data_ptr(), handle, C.byref(off))
+        # every rank takes part in the gather even if its export failed (no mismatched collectives)
+        mine = (bytes(handle), int(off.value)) if st == 0 else None
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        if any(e is None for e in everyone):
+            bad = [r for r, e in enumerate(everyone) if e is None]
+            raise RuntimeError(f"irr_peer_export failed on rank(s) {bad} (status here: {st})")
+        ptrs: List[int] = []
+        for r, (h, o) in enumerate(everyone):
+            if r == self.rank:
+                ptrs.append(self.buf.data_ptr())
+                continue
+            base = C.c_void_p()
+            hb = (C.c_uint8 * 64).from_buffer_copy(h)
+            with torch.cuda.device(self.device):
+                _lib.check(lib.irr_peer_import(hb, C.byref(base)), "irr_peer_import")
+            self._imported.append(int(base.value))
+            ptrs.append(int(base.value) + o)
+        return ptrs
+
+    def fits(self, Q: int, k: int) -> bool:
+        return _ops.topk_exchange_bytes(self.world, Q, k) <= self.nbytes
+
+    def exchange_merge(self, vals: torch.Tensor, idx: torch.Tensor,
+                       out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                       ) -> Tuple[torch.Tensor, torch.Tensor]:
+        Q, k = vals.shape
+        return _ops.topk_exchange_merge(vals, idx, self.ptrs, self.rank, Q, k, self.nbytes,
+                                        _lib.IRR_XCHG_FUSED, self.device, out)
+
+    def close(self) -> None:
+        """Collective: no rank may still be storing into a buffer that is about to be unmapped."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            for base in self._imported:
+                lib.irr_peer_close(base)
+        self._imported = []
+        dist.barrier(self.group)
+        self.handle = None
+        self.buf = None
+
+
+def _agree(ok: bool, group: Optional[dist.ProcessGroup], device: torch.device) -> bool:
+    """True only if every rank of the group says True."""
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
+
+
 class ShardedGallery:
     """This rank's shard of a row-sharded gallery plus the process group it is sharded over."""
 
     def __init__(self, local_embeddings: torch.Tensor, total_rows: int,
                  group: Optional[dist.ProcessGroup] = None, eps: float = 1e-6,
-                 cache_norms: bool = True) -> None:
+                 cache_norms: bool = True, exchange: str = "auto") -> None:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        exchange = os.environ.get("IRR_EXCHANGE", exchange)
+        if exchange not in ("auto", "peer", "collective"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'collective'")
+        self._exchange_mode = exchange
+        self._peer: Optional[PeerExchange] = None
+        self._peer_failed = False
+        self.exchange_error: Optional[str] = None
         lo, hi = shard_bounds(total_rows, self.world, self.rank)
         if local_embeddings.shape[0] != hi - lo:
             raise ValueError(
@@ -90,11 +208,72 @@ class ShardedGallery:
         lo, hi = shard_bounds(full_gallery.shape[0], dist.get_world_size(group), dist.get_rank(group))
         return cls(full_gallery[lo:hi], full_gallery.shape[0], group, **kw)
 
+    def close(self) -> None:
+        """Collective: release the peer-exchange buffers (no-op for the collective transport)."""
+        if self._peer is not None:
+            self._peer.close()
+            self._peer = None
+
+    @property
+    def transport(self) -> str:
+        """'peer' once a search went over peer memory, else 'collective' (what the next search
+        will use is decided on first use when exchange='auto')."""
+        return "peer" if self._peer is not None else "collective"
+
+    def _peer_exchange(self, Q: int, k: int) -> Optional[PeerExchange]:
+        """The peer transport sized for (Q, k), or None if this group uses the collective.  Growing
+        or creating the buffers is collective; every rank takes the same branch because Q, k and
+        the agreed outcome are the same everywhere."""
+        dev = self.local.embeddings.device
+        if (self._exchange_mode == "collective" or self._peer_failed or dev.type != "cuda"
+                or self.world > _lib.IRR_MAX_PEERS):
+            return None
+        if self._peer is not None and self._peer.fits(Q, k):
+            return self._peer
+        need = max(2 * _ops.topk_exchange_bytes(self.world, Q, k), 1 << 20)
+        if self._peer is not None:
+            self._peer.close()
+            self._peer = None
+        errs = []
+        for mapping in os.environ.get("IRR_PEER_MAPPING", "symm,ipc").split(","):
+            peer, err = None, None
+            try:
+                peer = PeerExchange(self.group, dev, need, mapping.strip())
+            except Exception as e:  # noqa: BLE001 - any mapping failure selects the next option
+                err = f"{mapping}: {type(e).__name__}: {e}"
+            if _agree(peer is not None, self.group, dev):
+                peer.activate()
+                self._peer = peer
+                return peer
+            errs.append(err or f"{mapping}: another rank could not map peer memory")
+        self._peer_failed = True
+        self.exchange_error = "; ".join(errs)
+        if self._exchange_mode == "peer":
+            raise RuntimeError(f"exchange='peer' requested but unavailable: {self.exchange_error}")
+        return None
+
+    def capture(self, num_queries: int, k: int) -> CapturedSearch:
+        """Collective: record the sharded search for a fixed batch shape as a CUDA graph on every
+        rank (local top-k + the peer-memory exchange kernel; replay = one launch per rank).  Needs
+        the peer transport for world > 1 — a collective library call is not recorded here."""
+        emb = self.local.embeddings
+        if self.world > 1 and self._peer_exchange(num_queries, k) is None:
+            raise RuntimeError("capture() needs the peer-memory exchange (exchange='peer'/'auto' on "
+                               f"GPUs of one box); unavailable: {self.exchange_error}")
+        return CapturedSearch(lambda q, kk: self.search(q, kk), num_queries, emb.shape[1], k,
+                              emb.dtype, emb.device)
+
     def search(self, queries: torch.Tensor, k: int) -> TopK:
         if k > self.total_rows:
             raise RuntimeError("selected index k out of range")
         if self.world == 1:
             return self.local.search(queries, k, allow_short=True)
+        peer = self._peer_exchange(queries.shape[0], k)
+        if peer is not None:
+            # local top-k, then ONE kernel: store into every peer over NVLink, flag, wait, merge
+            lv, li = self.local.search(queries, k, allow_short=True)
+            mv, mi = peer.exchange_merge(lv, li)
+            return TopK(mv, mi)
         # the local top-k writes straight into this rank's packed message, ONE all-gather moves
         # the G messages, and the merge kernel reads them in place (irr_topk_merge_strided)
         Q = queries.shape[0]

@@ -135,6 +135,56 @@ IRR_API irr_status irr_topk_merge_strided(const float* cand_val, int64_t val_ran
                                           int64_t* out_idx, irr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Peer-memory exchange fused with the merge (K3x) — the sharded gallery's one exchange step
+ *  without a collective library: every rank owns an exchange buffer of
+ * irr_topk_exchange_bytes() that is mapped into all G processes of the box (CUDA VMM / symmetric
+ * memory, done by the caller; zero-filled once, then a barrier, before its first use).
+ * peer_bufs: HOST array of the G device pointers as seen from THIS process, peer_bufs[rank] being
+ * this rank's own buffer.  One kernel stores this rank's [Q,k] list into slot `rank` of every
+ * buffer over NVLink, publishes the call's epoch to each peer (st.release.sys), waits until all G
+ * lists of the epoch have landed locally (ld.acquire.sys, watchdog IRR_EXCHANGE_TIMEOUT_MS,
+ * default 30 s -> trap) and merges them like irr_topk_merge.  Every rank of the group must make
+ * the same sequence of calls (same G, Q, k) on ONE stream per buffer; the epoch lives in the
+ * buffer, so the launch is CUDA-graph capturable.  G <= IRR_MAX_PEERS.
+ * mode: IRR_XCHG_FUSED the call described above; IRR_XCHG_PUSH store + publish only;
+ *       IRR_XCHG_MERGE wait + merge of the epoch last pushed (PUSH then MERGE == FUSED; used to
+ *       stage the protocol, e.g. several virtual ranks on one device in the tests).
+ * ------------------------------------------------------------------------------------------ */
+#define IRR_MAX_PEERS 16
+enum { IRR_XCHG_FUSED = 0, IRR_XCHG_PUSH = 1, IRR_XCHG_MERGE = 2 };
+IRR_API size_t irr_topk_exchange_bytes(int32_t G, int64_t Q, int32_t k);
+IRR_API irr_status irr_topk_exchange_merge(const float* local_val, const int64_t* local_idx,
+                                           void* const* peer_bufs, int32_t G, int32_t rank,
+                                           int64_t Q, int32_t k, size_t buf_bytes, int32_t mode,
+                                           float* out_val, int64_t* out_idx, irr_stream_t stream);
+
+/* Host plumbing for mapping one rank's exchange buffer into another process of the same box with
+ * CUDA IPC (the alternative to symmetric memory when the caller's allocator is cudaMalloc-backed).
+ * export: handle (64 bytes, cudaIpcMemHandle_t) of the allocation containing dev_ptr + dev_ptr's
+ *         byte offset inside it;  import: open a handle exported by ANOTHER process (peer access
+ *         is enabled lazily), *mapped_base is what irr_peer_close takes, the buffer is at
+ *         *mapped_base + offset.  These three are the only entry points that touch the driver's
+ *         memory-mapping state; none of them launches work. */
+IRR_API irr_status irr_peer_export(const void* dev_ptr, uint8_t handle_out[64], uint64_t* offset_out);
+IRR_API irr_status irr_peer_import(const uint8_t handle[64], void** mapped_base);
+IRR_API irr_status irr_peer_close(void* mapped_base);
+
+/* The whole sharded search in one call: irr_cosine_topk on this rank's gallery shard (rows
+ * [idx_offset, idx_offset + N_local) of the global gallery) followed by irr_topk_exchange_merge
+ * (IRR_XCHG_FUSED).  Replaces the same reference loop as irr_cosine_topk over a gallery that is
+ * row-sharded across the G GPUs of one box; out_* hold the GLOBAL top-k on every rank.
+ * workspace: irr_cosine_topk_sharded_workspace_bytes (local search workspace + the local lists). */
+IRR_API size_t irr_cosine_topk_sharded_workspace_bytes(int64_t Q, int64_t N_local, int32_t D,
+                                                       int32_t k, irr_dtype dt);
+IRR_API irr_status irr_cosine_topk_sharded(const void* q, const void* g_local,
+                                           const float* g_inv_norm, int64_t Q, int64_t N_local,
+                                           int32_t D, int32_t k, irr_dtype dt, float eps,
+                                           int64_t idx_offset, void* const* peer_bufs, int32_t G,
+                                           int32_t rank, size_t buf_bytes, float* out_val,
+                                           int64_t* out_idx, void* workspace,
+                                           size_t workspace_bytes, irr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * top-1 / top-k hit accounting — replaces the per-row Python tests
  *   class flavour    train/train_efficient_cos_con_ce_loss.py:279-281,390-392
  *   instance flavour inference/inference.py:237,242

@@ -90,6 +90,33 @@ def test_argument_validation_without_a_device():
     assert lib.irr_cosine_topk(None, None, None, 0, 4, 8, 1, 0, 1e-6, 0, p16, p16, None, 0, None) == 0
 
 
+def test_exchange_entry_points_validate_without_a_device():
+    lib = _lib.load()
+    buf = C.create_string_buffer(4096)
+    p16 = (C.addressof(buf) + 15) // 16 * 16
+    # layout: header + two halves of G slots [fp32 Q*k | pad16 | int64 Q*k]
+    assert lib.irr_topk_exchange_bytes(8, 4096, 3) == 512 + 2 * 8 * (4096 * 3 * 12)
+    assert lib.irr_topk_exchange_bytes(2, 1, 1) >= 512 + 2 * 2 * 32
+    assert lib.irr_topk_exchange_bytes(17, 1, 1) == 0          # > IRR_MAX_PEERS
+    assert lib.irr_topk_exchange_bytes(0, 1, 1) == 0
+    assert int(re.search(r"#define IRR_MAX_PEERS (\d+)", HEADER).group(1)) == _lib.IRR_MAX_PEERS
+    ptrs = (C.c_void_p * 2)(p16, p16)
+    call = lib.irr_topk_exchange_merge
+    assert call(p16, p16, None, 2, 0, 4, 3, 1 << 20, 0, p16, p16, None) == -1      # no pointer table
+    assert call(p16, p16, ptrs, 2, 2, 4, 3, 1 << 20, 0, p16, p16, None) == -1      # rank out of range
+    assert call(p16, p16, ptrs, 2, 0, 4, 3, 1 << 20, 7, p16, p16, None) == -1      # unknown mode
+    assert call(p16, p16, ptrs, 2, 0, 4, 257, 1 << 20, 0, p16, p16, None) == -5    # k too large
+    assert call(None, None, ptrs, 2, 0, 4, 3, 1 << 20, 0, p16, p16, None) == -1    # fused needs lists
+    assert call(p16, p16, ptrs, 2, 0, 4, 3, 600, 0, p16, p16, None) == -4          # buffer too small
+    bad = (C.c_void_p * 2)(p16, None)
+    assert call(p16, p16, bad, 2, 0, 4, 3, 1 << 20, 0, p16, p16, None) == -1       # unmapped peer
+    assert lib.irr_cosine_topk_sharded_workspace_bytes(64, 1000, 1536, 3, 1) > \
+        lib.irr_cosine_topk_workspace_bytes(64, 1000, 1536, 3, 1)
+    assert lib.irr_peer_export(None, None, None) == -1
+    assert lib.irr_peer_import(None, None) == -1
+    assert lib.irr_peer_close(None) == -1
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libirr_b200.so")

@@ -501,6 +501,60 @@ def test_packed_exchange_buffer_merge(k):
     assert torch.equal(i.cpu(), wi) and torch.equal(v.cpu(), wv)
 
 
+@pytest.mark.parametrize("G,Q,k", [(4, 21, 3), (8, 300, 10), (2, 5, 150), (3, 1, 1), (8, 4096, 3)])
+def test_peer_exchange_protocol_on_one_device(G, Q, k, monkeypatch):
+    """irr_topk_exchange_merge (csrc/topk_exchange.cu) with G virtual ranks on one device: every
+    rank owns a buffer, all G buffers are 'mapped' (same address space here).  Per round, ranks
+    1..G-1 push (store + publish epoch), rank 0 runs the FUSED kernel (push + wait + merge; all its
+    peers have already published, so it cannot block), ranks 1..G-1 then wait + merge.  Three
+    rounds with fresh lists exercise both buffer halves and the self-resetting epoch words."""
+    from imageretrievalresearch_b200 import _lib
+    monkeypatch.setenv("IRR_EXCHANGE_TIMEOUT_MS", "2000")   # a protocol bug traps instead of hanging
+    dev = torch.device("cuda", 0)
+    nbytes = _ops.topk_exchange_bytes(G, Q, k) + 4096       # not the exact size: halves must adapt
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(G)]
+    ptrs = [b.data_ptr() for b in bufs]
+    for rnd in range(3):
+        torch.manual_seed(1000 * rnd + G * 10 + k)
+        vals = torch.randn(G, Q, k).sort(dim=2, descending=True).values
+        idx = torch.stack([torch.randperm(5000)[:k].sort().values + g * 5000
+                           for g in range(G) for _ in range(Q)]).view(G, Q, k)
+        if G > 1:
+            vals[0, :, 0] = vals[1, :, 0]
+            idx[G - 1, ::3, k - 1] = -1
+            vals[G - 1, ::3, k - 1] = -float("inf")
+        dv, di = vals.cuda(), idx.cuda()
+        for r in range(1, G):
+            _ops.topk_exchange_merge(dv[r], di[r], ptrs, r, Q, k, nbytes, _lib.IRR_XCHG_PUSH, dev)
+        outs = [_ops.topk_exchange_merge(dv[0], di[0], ptrs, 0, Q, k, nbytes, _lib.IRR_XCHG_FUSED, dev)]
+        for r in range(1, G):
+            outs.append(_ops.topk_exchange_merge(None, None, ptrs, r, Q, k, nbytes,
+                                                 _lib.IRR_XCHG_MERGE, dev))
+        wv, wi = ref.merge_candidates(vals, idx, k)
+        for r, (v, i) in enumerate(outs):
+            assert torch.equal(i.cpu(), wi) and torch.equal(v.cpu(), wv), (rnd, r)
+    epochs = [int(b[256:260].view(torch.int32).item()) for b in bufs]
+    assert epochs == [3] * G
+
+
+@pytest.mark.parametrize("Q,k,dtype", [(1, 3, torch.bfloat16), (64, 10, torch.bfloat16),
+                                       (300, 3, torch.bfloat16), (7, 3, torch.float32)])
+def test_captured_search_replays_bit_identically(Q, k, dtype):
+    """Gallery.capture: the search recorded as a CUDA graph returns, replay after replay and for
+    new query batches, exactly what the eager call returns."""
+    N, D = 20_000, 256
+    q0, gal = synthetic.iid_gallery(N, D, Q, seed=5, dtype=dtype)
+    g = irr.Gallery(gal.cuda())
+    cap = g.capture(Q, k)
+    for seed in (6, 7, 8):
+        q, _ = synthetic.iid_gallery(8, D, Q, seed=seed, dtype=dtype)
+        got = cap(q.cuda())
+        want = g.search(q.cuda(), k)
+        assert torch.equal(got.indices, want.indices) and torch.equal(got.values, want.values)
+    again = cap()
+    assert torch.equal(again.indices, want.indices)
+
+
 def test_dedup_edge_cases():
     # fewer distinct classes than requested, padding entries, n_distinct = 1
     idx = torch.tensor([[0, 1, 2, 3], [4, 4, 5, -1], [6, -1, -1, -1]])
