@@ -135,6 +135,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
 }
+// Same contract for waits made by MANY threads at once (whole warps waiting for bulk-copied data):
+// try_wait with a suspend-time hint parks the thread in hardware until the phase completes (or the
+// hint expires) instead of spinning through issue slots the arithmetic warps need.
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_wait_parked_slow(uint32_t bar, uint32_t parity, int tag) {
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait_suspend(bar, parity, 20000u)) {
+    if (global_timer_ns() - t0 > 4000000000ull) {
+      printf("irr_b200: mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, tag, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_parked_slow(bar, parity, tag);
+}
 
 // ---- TMA -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
@@ -156,6 +186,14 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
           "r"(smem_dst),
       "l"(gsrc), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_hint(uint32_t smem_dst, const void* gsrc, uint32_t bytes,
+                                                  uint32_t bar, uint64_t cache_policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], "
+      "%2, [%3], %4;" ::"r"(smem_dst),
+      "l"(gsrc), "r"(bytes), "r"(bar), "l"(cache_policy)
       : "memory");
 }
 // L2 eviction-priority policies for the .L2::cache_hint operand (createpolicy encodings)

@@ -6,15 +6,21 @@
 //   the logged paired cosine scores         train/train_efficient_cos_con_ce_loss.py:377-382
 // and their autograd backward (closed forms: SURVEY.md §A.1).
 //
-// HBM-bound design: every input byte crosses L2->SM exactly once.  One warp owns one row triplet at
-// a time; lane 0 stages the three rows into the warp's private shared-memory slot with 1-D bulk
-// async copies (cp.async.bulk, completion on an mbarrier) one row ahead of the arithmetic; the
-// warp reduces seven sums with 128-bit shared loads + shuffles, turns them into the four loss terms
-// and seven gradient coefficients, and streams dq/dp/dn straight from the staged rows with 128-bit
-// stores.  Each gradient is a per-row linear combination of the three rows:
+// HBM-bound design: every input byte crosses L2->SM exactly once.  A group of four warps owns one
+// row triplet at a time (up to eight groups per CTA, one CTA per SM); the group's first lane stages
+// the three rows into the group's shared-memory slot with 1-D bulk async copies (cp.async.bulk,
+// completion on an mbarrier) one row ahead of the arithmetic; each thread reduces seven sums over
+// its 128-bit vectors (LDS.128 + shuffles + a fixed-order add of the four warp partials), every
+// thread derives the four loss terms and seven gradient coefficients from the same sums, and the
+// group streams dq/dp/dn straight from the staged rows with 128-bit stores.  (One warp per row —
+// the first version — left 1.5 warps per scheduler: ncu showed the kernel bound by its own
+// instruction latency at 19 % issue utilisation, not by HBM.)  Each gradient is a per-row linear
+// combination of the three rows:
 //   dq = aqq*q + aqp*p + aqn*n     dp = app*p + aqp*q     dn = ann*n + aqn*q
-// Loss scalars: fixed row->warp assignment, per-warp partials, last-CTA-done fixed-order reduction
+// Loss scalars: fixed row->group assignment, per-group partials, last-CTA-done fixed-order reduction
 // (deterministic; the sync word resets itself, see irr_b200.h).
+#include <stdlib.h>
+
 #include "irr_common.cuh"
 #include "irr_kernels.h"
 
@@ -22,46 +28,77 @@ namespace irr {
 namespace {
 
 constexpr int LSTAGES = 2;
-constexpr int MAX_WARPS = 16;
+constexpr int GW = 4;            // warps that share one row triplet
+constexpr int GT = GW * 32;
+constexpr int MAX_GROUPS = 8;    // row-triplet slots (groups of GW warps) per CTA
 constexpr int SMEM_BUDGET = 220 * 1024;
 
 struct Coef {
   float aqq, aqp, aqn, app, ann;
 };
 
+// One 16-byte vector as packed fp32 pairs: the arithmetic below runs on Blackwell's packed
+// FFMA2 / FMUL2 (two fp32 lanes per instruction), which halves the issue slots of a kernel whose
+// limit next to HBM is instruction issue.
 template <bool BF16>
 struct Vec {
-  static constexpr int N = BF16 ? 8 : 4;
-  __device__ static __forceinline__ void unpack(const uint4& u, float (&f)[N]) {
+  static constexpr int N = BF16 ? 8 : 4;   // elements per vector
+  static constexpr int H = N / 2;          // float2 pairs per vector
+  __device__ static __forceinline__ void unpack(const uint4& u, float2 (&f)[H]) {
     if constexpr (BF16) {
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        f[2 * j] = bf16lo(w[j]);
-        f[2 * j + 1] = bf16hi(w[j]);
-      }
+      for (int j = 0; j < 4; ++j) f[j] = make_float2(bf16lo(w[j]), bf16hi(w[j]));
     } else {
-      f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y);
-      f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+      f[0] = make_float2(__uint_as_float(u.x), __uint_as_float(u.y));
+      f[1] = make_float2(__uint_as_float(u.z), __uint_as_float(u.w));
     }
   }
-  __device__ static __forceinline__ uint4 pack(const float (&f)[N]) {
+  __device__ static __forceinline__ uint4 pack(const float2 (&f)[H]) {
     uint4 u;
     if constexpr (BF16) {
       uint32_t w[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(f[j].x, f[j].y);
         w[j] = *reinterpret_cast<const uint32_t*>(&h);
       }
       u = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-      u = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
-                     __float_as_uint(f[3]));
+      u = make_uint4(__float_as_uint(f[0].x), __float_as_uint(f[0].y), __float_as_uint(f[1].x),
+                     __float_as_uint(f[1].y));
     }
     return u;
   }
 };
+
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// Sum eight values across the warp with 15 shuffles instead of 40: each butterfly step halves the
+// number of values a lane carries (the lane keeps the half selected by its own lane bit and sends
+// the other half).  Returns in lane l the warp total of value ((l>>4)&1)*4 + ((l>>3)&1)*2 + ((l>>2)&1);
+// the four lanes that share l>>2 hold the same number.  Fixed order: deterministic.
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+  float a[4], b[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = h16 ? v[i] : v[i + 4];
+    const float keep = h16 ? v[i + 4] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = h8 ? a[i] : a[i + 2];
+    const float keep = h8 ? a[i + 2] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const float send = h4 ? b[0] : b[1];
+  float r = (h4 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, send, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
 
 struct RowSums {
   float qq, pp, nn, qp, qn, dp, dn;
@@ -138,164 +175,215 @@ struct KParams {
   float *losses, *pair_cos, *row_stats;
   uint4 *dq, *dp, *dn;
   unsigned int* sync_word;
-  float* partials;  // [gridDim.x * warps][4]
+  float* partials;  // [gridDim.x * groups][4], 16-byte aligned
+  int hints;        // measurement knob IRR_LOSS_HINTS: 1 = evict-first loads, 2 = streaming stores
 };
 
 template <bool BF16, bool TRIPLET>
-__global__ void __launch_bounds__(MAX_WARPS * 32, 1)
+__global__ void __launch_bounds__(MAX_GROUPS * GT, 1)
 loss_fwd_bwd_kernel(const KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warps = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = blockDim.x / GT;
+  const int grp = threadIdx.x / GT;   // row-triplet slot this thread's group owns
+  const int gt = threadIdx.x % GT;    // thread within the group
+  const int gwarp = gt >> 5, lane = gt & 31;
   constexpr int ROWS = TRIPLET ? 3 : 2;
   const uint32_t row_bytes = static_cast<uint32_t>(P.vec_per_row) * 16u;
   const uint32_t slot_bytes = ROWS * row_bytes;
-  // [warps][LSTAGES][ROWS][row_bytes] then the mbarriers
-  uint8_t* my_slots = smem + static_cast<size_t>(warp) * LSTAGES * slot_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(warps) * LSTAGES * slot_bytes);
-  const uint32_t bar0 = smem_u32(bars + warp * LSTAGES);
+  // [groups][LSTAGES][ROWS][row_bytes] | mbarriers [groups][LSTAGES] | scratch [groups][GW+1][8]
+  uint8_t* my_slots = smem + static_cast<size_t>(grp) * LSTAGES * slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(groups) * LSTAGES * slot_bytes);
+  float* scratch = reinterpret_cast<float*>(bars + groups * LSTAGES) + grp * ((GW + 1) * 8);
+  const uint32_t bar0 = smem_u32(bars + grp * LSTAGES);
 
-  if (lane == 0) {
+  if (gt == 0) {
     for (int s = 0; s < LSTAGES; ++s) mbar_init(bar0 + 8u * s, 1);
     fence_mbar_init();
   }
   __syncthreads();
 
-  const int64_t gw = static_cast<int64_t>(blockIdx.x) * warps + warp;
-  const int64_t tw = static_cast<int64_t>(gridDim.x) * warps;
+  const int64_t gg = static_cast<int64_t>(blockIdx.x) * groups + grp;
+  const int64_t tg = static_cast<int64_t>(gridDim.x) * groups;
 
   auto issue = [&](int64_t row, int s) {
     const uint32_t dst = smem_u32(my_slots + static_cast<size_t>(s) * slot_bytes);
     const uint32_t bar = bar0 + 8u * s;
     mbar_arrive_expect_tx(bar, slot_bytes);
-    bulk_load_1d(dst, P.q + row * P.vec_per_row, row_bytes, bar);
-    bulk_load_1d(dst + row_bytes, P.p + row * P.vec_per_row, row_bytes, bar);
-    if (TRIPLET) bulk_load_1d(dst + 2 * row_bytes, P.n + row * P.vec_per_row, row_bytes, bar);
+    if (P.hints & 1) {
+      bulk_load_1d_hint(dst, P.q + row * P.vec_per_row, row_bytes, bar, kPolicyEvictFirst);
+      bulk_load_1d_hint(dst + row_bytes, P.p + row * P.vec_per_row, row_bytes, bar, kPolicyEvictFirst);
+      if (TRIPLET)
+        bulk_load_1d_hint(dst + 2 * row_bytes, P.n + row * P.vec_per_row, row_bytes, bar, kPolicyEvictFirst);
+    } else {
+      bulk_load_1d(dst, P.q + row * P.vec_per_row, row_bytes, bar);
+      bulk_load_1d(dst + row_bytes, P.p + row * P.vec_per_row, row_bytes, bar);
+      if (TRIPLET) bulk_load_1d(dst + 2 * row_bytes, P.n + row * P.vec_per_row, row_bytes, bar);
+    }
   };
 
-  if (lane == 0) {
+  if (gt == 0) {
     for (int s = 0; s < LSTAGES; ++s) {
-      const int64_t row = gw + s * tw;
+      const int64_t row = gg + s * tg;
       if (row < P.B) issue(row, s);
     }
   }
-  __syncwarp();
 
-  float lsum[4] = {0.f, 0.f, 0.f, 0.f};
-  constexpr int VN = Vec<BF16>::N;
+  float lsum[4] = {0.f, 0.f, 0.f, 0.f};   // meaningful in the group's first warp only
+  constexpr int VH = Vec<BF16>::H;
+  const float2 neg1 = splat2(-1.0f);
+  float* coef_s = scratch + GW * 8;       // 8 floats: the row's gradient coefficients
   int it = 0;
-  for (int64_t row = gw; row < P.B; row += tw, ++it) {
+  for (int64_t row = gg; row < P.B; row += tg, ++it) {
     const int s = it % LSTAGES;
     const uint32_t parity = (it / LSTAGES) & 1;
-    mbar_wait(bar0 + 8u * s, parity, 500 + s);
+    mbar_wait_parked(bar0 + 8u * s, parity, 500 + s);
     const uint4* sq = reinterpret_cast<const uint4*>(my_slots + static_cast<size_t>(s) * slot_bytes);
     const uint4* sp = sq + P.vec_per_row;
     const uint4* sn = sp + P.vec_per_row;
 
-    RowSums S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int v = lane; v < P.vec_per_row; v += 32) {
-      float fq[VN], fp[VN], fn[VN];
+    // ---- seven sums: this thread's 16-byte vectors (even / odd elements in the two packed lanes),
+    // then the warp (warp_reduce8), then the group's four warps (first warp, fixed order) ----
+    float2 aqq = splat2(0.f), app = aqq, ann = aqq, aqp = aqq, aqn = aqq, adp = aqq, adn = aqq;
+    for (int v = gt; v < P.vec_per_row; v += GT) {
+      float2 fq[VH], fp[VH], fn[VH];
       Vec<BF16>::unpack(sq[v], fq);
       Vec<BF16>::unpack(sp[v], fp);
       if (TRIPLET) Vec<BF16>::unpack(sn[v], fn);
 #pragma unroll
-      for (int j = 0; j < VN; ++j) {
-        S.qq = fmaf(fq[j], fq[j], S.qq);
-        S.pp = fmaf(fp[j], fp[j], S.pp);
-        S.qp = fmaf(fq[j], fp[j], S.qp);
-        const float d = fp[j] - fq[j];
-        S.dp = fmaf(d, d, S.dp);
+      for (int j = 0; j < VH; ++j) {
+        aqq = __ffma2_rn(fq[j], fq[j], aqq);
+        app = __ffma2_rn(fp[j], fp[j], app);
+        aqp = __ffma2_rn(fq[j], fp[j], aqp);
+        const float2 d = __ffma2_rn(fq[j], neg1, fp[j]);   // p - q, exact like a subtraction
+        adp = __ffma2_rn(d, d, adp);
         if (TRIPLET) {
-          S.nn = fmaf(fn[j], fn[j], S.nn);
-          S.qn = fmaf(fq[j], fn[j], S.qn);
-          const float e = fn[j] - fq[j];
-          S.dn = fmaf(e, e, S.dn);
+          ann = __ffma2_rn(fn[j], fn[j], ann);
+          aqn = __ffma2_rn(fq[j], fn[j], aqn);
+          const float2 e = __ffma2_rn(fq[j], neg1, fn[j]);
+          adn = __ffma2_rn(e, e, adn);
         }
       }
     }
-    S.qq = warp_sum(S.qq); S.pp = warp_sum(S.pp); S.qp = warp_sum(S.qp); S.dp = warp_sum(S.dp);
-    if (TRIPLET) { S.nn = warp_sum(S.nn); S.qn = warp_sum(S.qn); S.dn = warp_sum(S.dn); }
-
-    RowOut o;
-    if (TRIPLET) {
-      o = triplet_row(S, P.m_cos, P.m_con, P.w);
-    } else {
-      const float y = __ldg(P.label + (P.label_count == 1 ? 0 : row));
-      o = pair_row(S, P.kind, y, P.kind == IRR_LOSS_CONTRASTIVE ? P.m_con : P.m_cos, P.w[0]);
+    {
+      const float part[8] = {aqq.x + aqq.y, app.x + app.y, ann.x + ann.y, aqp.x + aqp.y,
+                             aqn.x + aqn.y, adp.x + adp.y, adn.x + adn.y, 0.f};
+      const float r = warp_reduce8(part, lane);
+      if ((lane & 3) == 0) scratch[gwarp * 8 + (lane >> 2)] = r;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) lsum[j] += o.l[j];
+    named_bar_sync(1 + grp, GT);
 
-    if (lane == 0) {
-      if (P.pair_cos) {
-        const float nq = fmaxf(sqrtf(S.qq), P.pair_eps);
-        P.pair_cos[row] = S.qp / (nq * fmaxf(sqrtf(S.pp), P.pair_eps));
-        if (TRIPLET) P.pair_cos[P.B + row] = S.qn / (nq * fmaxf(sqrtf(S.nn), P.pair_eps));
+    if (gwarp == 0) {
+      // order of the eight slots = warp_reduce8's value index: qq pp nn qp | qn dp dn -
+      const float4* sc = reinterpret_cast<const float4*>(scratch);
+      float4 a = sc[0], b = sc[1];
+#pragma unroll
+      for (int w = 1; w < GW; ++w) {
+        const float4 c = sc[2 * w], d = sc[2 * w + 1];
+        a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+        b.x += d.x; b.y += d.y; b.z += d.z;
       }
-      if (P.row_stats) {
-        float4* rs = reinterpret_cast<float4*>(P.row_stats + row * IRR_ROW_STATS);
-        rs[0] = make_float4(S.qq, S.pp, S.nn, S.qp);
-        rs[1] = make_float4(S.qn, S.dp, S.dn, 0.f);
+      const RowSums S = {a.x, a.y, a.z, a.w, b.x, b.y, b.z};
+      RowOut o;
+      if (TRIPLET) {
+        o = triplet_row(S, P.m_cos, P.m_con, P.w);
+      } else {
+        const float y = __ldg(P.label + (P.label_count == 1 ? 0 : row));
+        o = pair_row(S, P.kind, y, P.kind == IRR_LOSS_CONTRASTIVE ? P.m_con : P.m_cos, P.w[0]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) lsum[j] += o.l[j];
+      if (lane == 0) {
+        float4* cs = reinterpret_cast<float4*>(coef_s);
+        cs[0] = make_float4(o.c.aqq, o.c.aqp, o.c.aqn, o.c.app);
+        cs[1] = make_float4(o.c.ann, 0.f, 0.f, 0.f);
+        if (P.pair_cos) {
+          const float nq = fmaxf(sqrtf(S.qq), P.pair_eps);
+          P.pair_cos[row] = S.qp / (nq * fmaxf(sqrtf(S.pp), P.pair_eps));
+          if (TRIPLET) P.pair_cos[P.B + row] = S.qn / (nq * fmaxf(sqrtf(S.nn), P.pair_eps));
+        }
+        if (P.row_stats) {
+          float4* rs = reinterpret_cast<float4*>(P.row_stats + row * IRR_ROW_STATS);
+          rs[0] = make_float4(S.qq, S.pp, S.nn, S.qp);
+          rs[1] = make_float4(S.qn, S.dp, S.dn, 0.f);
+        }
       }
     }
 
     if (P.dq) {
+      named_bar_sync(1 + grp, GT);   // coefficients published
+      const float4 c0 = reinterpret_cast<const float4*>(coef_s)[0];
+      const float2 kqq = splat2(c0.x), kqp = splat2(c0.y), kqn = splat2(c0.z), kpp = splat2(c0.w);
+      const float2 knn = splat2(coef_s[4]);
       uint4* gq = P.dq + row * P.vec_per_row;
       uint4* gp = P.dp + row * P.vec_per_row;
       uint4* gn = TRIPLET ? P.dn + row * P.vec_per_row : nullptr;
-      for (int v = lane; v < P.vec_per_row; v += 32) {
-        float fq[VN], fp[VN], fn[VN], oq[VN], op[VN], on[VN];
+      for (int v = gt; v < P.vec_per_row; v += GT) {
+        float2 fq[VH], fp[VH], fn[VH], oq[VH], op[VH], on[VH];
         Vec<BF16>::unpack(sq[v], fq);
         Vec<BF16>::unpack(sp[v], fp);
         if (TRIPLET) Vec<BF16>::unpack(sn[v], fn);
 #pragma unroll
-        for (int j = 0; j < VN; ++j) {
-          float a = fmaf(o.c.aqq, fq[j], o.c.aqp * fp[j]);
-          op[j] = fmaf(o.c.app, fp[j], o.c.aqp * fq[j]);
+        for (int j = 0; j < VH; ++j) {
+          float2 a = __ffma2_rn(kqq, fq[j], __fmul2_rn(kqp, fp[j]));
+          op[j] = __ffma2_rn(kpp, fp[j], __fmul2_rn(kqp, fq[j]));
           if (TRIPLET) {
-            a = fmaf(o.c.aqn, fn[j], a);
-            on[j] = fmaf(o.c.ann, fn[j], o.c.aqn * fq[j]);
+            a = __ffma2_rn(kqn, fn[j], a);
+            on[j] = __ffma2_rn(knn, fn[j], __fmul2_rn(kqn, fq[j]));
           }
           oq[j] = a;
         }
-        gq[v] = Vec<BF16>::pack(oq);
-        gp[v] = Vec<BF16>::pack(op);
-        if (TRIPLET) gn[v] = Vec<BF16>::pack(on);
+        if (P.hints & 2) {
+          __stcs(gq + v, Vec<BF16>::pack(oq));
+          __stcs(gp + v, Vec<BF16>::pack(op));
+          if (TRIPLET) __stcs(gn + v, Vec<BF16>::pack(on));
+        } else {
+          gq[v] = Vec<BF16>::pack(oq);
+          gp[v] = Vec<BF16>::pack(op);
+          if (TRIPLET) gn[v] = Vec<BF16>::pack(on);
+        }
       }
     }
 
-    __syncwarp();  // every lane is done with the slot before it is refilled
-    const int64_t next = row + LSTAGES * tw;
-    if (lane == 0 && next < P.B) issue(next, s);
+    // the whole group is done with the slot (and with the scratch words) before it is refilled
+    named_bar_sync(1 + grp, GT);
+    const int64_t next = row + LSTAGES * tg;
+    if (gt == 0 && next < P.B) issue(next, s);
   }
 
-  // ---- deterministic reduction of the loss scalars ----
+  // ---- deterministic reduction of the loss scalars: one partial per group (fixed row -> group
+  // map), the last CTA to check in adds them in a fixed order ----
   constexpr int NL = TRIPLET ? 4 : 1;
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) P.partials[gw * 4 + j] = lsum[j];
-  }
-  __threadfence();
+  if (gt == 0)
+    reinterpret_cast<float4*>(P.partials)[gg] = make_float4(lsum[0], lsum[1], lsum[2], lsum[3]);
   __syncthreads();
   __shared__ int is_last;
+  __shared__ float4 red[MAX_GROUPS * GW];
   if (threadIdx.x == 0) {
+    __threadfence();   // cumulative: covers the group leaders' partials ordered by the barrier
     const unsigned int prev = atomicAdd(P.sync_word, 1u);
     is_last = (prev == gridDim.x - 1);
+    __threadfence();
   }
   __syncthreads();
-  if (is_last && warp == 0) {
-    __threadfence();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t i = lane; i < tw; i += 32) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] += __ldcg(P.partials + i * 4 + j);
+  if (is_last) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = threadIdx.x; i < tg; i += blockDim.x) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(P.partials) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int nw = blockDim.x >> 5;
+      float4 v = threadIdx.x < nw ? red[threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+      if (threadIdx.x == 0) {
+        const float r[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < NL; ++j) P.losses[j] = acc[j] * P.red_scale;
-      *P.sync_word = 0u;  // self-reset for the next call on this workspace
+        for (int j = 0; j < NL; ++j) P.losses[j] = r[j] * P.red_scale;
+        *P.sync_word = 0u;  // self-reset for the next call on this workspace
+      }
     }
   }
 }
@@ -319,7 +407,7 @@ loss_bwd_kernel(const BParams P) {
   const int lane = threadIdx.x & 31;
   const int64_t gw = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t tw = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-  constexpr int VN = Vec<BF16>::N;
+  constexpr int VH = Vec<BF16>::H;
   float w[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) w[j] = (TRIPLET || j == 0) ? __ldg(P.grad_out + j) * P.red_scale : 0.f;
@@ -340,18 +428,20 @@ loss_bwd_kernel(const BParams P) {
     uint4* gq = P.dq + row * P.vec_per_row;
     uint4* gp = P.dp + row * P.vec_per_row;
     uint4* gn = TRIPLET ? P.dn + row * P.vec_per_row : nullptr;
+    const float2 kqq = splat2(c.aqq), kqp = splat2(c.aqp), kqn = splat2(c.aqn), kpp = splat2(c.app),
+                 knn = splat2(c.ann);
     for (int v = lane; v < P.vec_per_row; v += 32) {
-      float fq[VN], fp[VN], fn[VN], oq[VN], op[VN], on[VN];
+      float2 fq[VH], fp[VH], fn[VH], oq[VH], op[VH], on[VH];
       Vec<BF16>::unpack(ldg_stream(sq + v), fq);
       Vec<BF16>::unpack(ldg_stream(sp + v), fp);
       if (TRIPLET) Vec<BF16>::unpack(ldg_stream(sn + v), fn);
 #pragma unroll
-      for (int j = 0; j < VN; ++j) {
-        float a = fmaf(c.aqq, fq[j], c.aqp * fp[j]);
-        op[j] = fmaf(c.app, fp[j], c.aqp * fq[j]);
+      for (int j = 0; j < VH; ++j) {
+        float2 a = __ffma2_rn(kqq, fq[j], __fmul2_rn(kqp, fp[j]));
+        op[j] = __ffma2_rn(kpp, fp[j], __fmul2_rn(kqp, fq[j]));
         if (TRIPLET) {
-          a = fmaf(c.aqn, fn[j], a);
-          on[j] = fmaf(c.ann, fn[j], c.aqn * fq[j]);
+          a = __ffma2_rn(kqn, fn[j], a);
+          on[j] = __ffma2_rn(knn, fn[j], __fmul2_rn(kqn, fq[j]));
         }
         oq[j] = a;
       }
@@ -363,34 +453,35 @@ loss_bwd_kernel(const BParams P) {
 }
 
 struct LaunchShape {
-  int warps, grid;
+  int groups, grid;
   size_t smem;
 };
 
-// warps per CTA from the shared-memory budget, then spread the rows over the SMs
+// row-triplet slots per CTA from the shared-memory budget, then spread the rows over the SMs
 bool shape_for(int64_t B, int32_t D, irr_dtype dt, bool triplet, LaunchShape* s) {
   const size_t row_bytes = static_cast<size_t>(D) * dtype_bytes(dt);
-  const size_t per_warp = LSTAGES * (triplet ? 3 : 2) * row_bytes + LSTAGES * 8;
-  int wmax = static_cast<int>(SMEM_BUDGET / per_warp);
-  if (wmax < 1) return false;
-  if (wmax > MAX_WARPS) wmax = MAX_WARPS;
+  const size_t per_group = LSTAGES * (triplet ? 3 : 2) * row_bytes + LSTAGES * 8 + (GW + 1) * 8 * sizeof(float);
+  int gmax = static_cast<int>(SMEM_BUDGET / per_group);
+  if (gmax < 1) return false;
+  if (gmax > MAX_GROUPS) gmax = MAX_GROUPS;
   const int sms = num_sms();
   int64_t want = (B + sms - 1) / sms;  // rows per SM if every SM takes part
-  int warps = static_cast<int>(want < 1 ? 1 : (want > wmax ? wmax : want));
-  int64_t grid = (B + warps - 1) / warps;
+  int groups = static_cast<int>(want < 1 ? 1 : (want > gmax ? gmax : want));
+  int64_t grid = (B + groups - 1) / groups;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  s->warps = warps;
+  s->groups = groups;
   s->grid = static_cast<int>(grid);
-  s->smem = static_cast<size_t>(warps) * per_warp;
+  s->smem = static_cast<size_t>(groups) * per_group;
   return true;
 }
 
 }  // namespace
 
 size_t loss_workspace_bytes(int64_t, int32_t, irr_dtype) {
-  // sync word (padded) + per-warp partials for the largest launch shape
-  return 256 + static_cast<size_t>(num_sms()) * MAX_WARPS * 4 * sizeof(float);
+  // sync word (padded) + per-group partials for the largest launch shape (sized generously: the
+  // previous per-warp layout's 16 entries per SM)
+  return 256 + static_cast<size_t>(num_sms()) * 16 * 4 * sizeof(float);
 }
 
 irr_status loss_fwd_bwd(const LossArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -420,13 +511,17 @@ irr_status loss_fwd_bwd(const LossArgs& a, void* ws, size_t ws_bytes, cudaStream
   P.dn = static_cast<uint4*>(a.dn);
   P.sync_word = static_cast<unsigned int*>(ws);
   P.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
+  {
+    const char* e = getenv("IRR_LOSS_HINTS");
+    P.hints = e ? atoi(e) : 1;   // evict-first loads measured +3 % (profiles/r01_notes.md)
+  }
 
 #define IRR_LAUNCH_LOSS(BF, TR)                                                                   \
   do {                                                                                            \
     auto kern = loss_fwd_bwd_kernel<BF, TR>;                                                      \
     IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                       static_cast<int>(sh.smem)));                                \
-    kern<<<sh.grid, sh.warps * 32, sh.smem, st>>>(P);                                             \
+    kern<<<sh.grid, sh.groups * GT, sh.smem, st>>>(P);                                             \
   } while (0)
   if (a.dt == IRR_BF16) {
     if (triplet) IRR_LAUNCH_LOSS(true, true); else IRR_LAUNCH_LOSS(true, false);
