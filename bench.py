@@ -7,11 +7,14 @@ Metric (BASELINE.json): top-k cosine queries/s at a 1M x 1536 gallery.  Workload
 over a 1,000,000 x 1536 bf16 synthetic gallery with Q=4096 queries per step (the configuration
 BASELINE.json's target is quoted on; it fits one GPU).  With N>1 the gallery is row-sharded over
 the N ranks (N/G rows each, so total work is fixed: "strong" scaling) and every step ends with the
-path's one exchange: an NCCL all-gather of the [Q,k] candidates and the merge kernel.
+path's one exchange of the [Q,k] candidates: ONE kernel per rank that stores its list into every
+peer over NVLink peer memory, flags, waits and merges (csrc/topk_exchange.cu); if peer memory
+cannot be mapped the ranks agree on an NCCL all-gather + merge kernel instead (`config.exchange`
+says which ran).
 
 A step = one search of all Q queries: inverse row norms of the gallery shard (recomputed every
 step: nothing is cached across steps), the tcgen05 top-k kernel, the partial-list merge, and for
-N>1 all-gather + candidate merge.  `value` times that with the queries resident in HBM; `e2e`
+N>1 the candidate exchange + merge.  `value` times that with the queries resident in HBM; `e2e`
 times the same call with the queries coming from pinned host memory and the [Q,k] results going
 back to pinned host memory inside the timed region (the gallery is the resident index, as in the
 reference where the embeddings live on the device: inference/training_analysis.ipynb:222).
@@ -348,7 +351,10 @@ def run_b200(a):
             "config": {"workload": workload_name(a, world), "Q": Q, "N": N, "D": D, "k": k,
                        "parallelism": f"gallery rows sharded x{world}",
                        "l2": "inputs larger than L2 (gallery shard streamed every step); no flush",
-                       "norms": "inverse gallery norms recomputed every step (no cached state)"},
+                       "norms": "inverse gallery norms recomputed every step (no cached state)",
+                       "exchange": (("peer-memory exchange+merge kernel (" + gallery._peer.mapping + ")")
+                                    if world > 1 and gallery.transport == "peer" else
+                                    ("nccl all-gather + merge kernel" if world > 1 else "none"))},
             "e2e": e2e, "gpu_launches": launches_per_step * a.steps, "clocks": clocks.summary(),
             "roofline": roof, "cpu_baseline": cpu,
         }
