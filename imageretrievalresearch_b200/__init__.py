@@ -12,6 +12,8 @@ from .losses import (ContrastiveLoss, CosineEmbeddingLoss, TripletFwdBwd, Triple
 from .producer_consumer import CEPair, cross_entropy_pair, get_fm
 from .retrieval import (CapturedSearch, CosineSimilarity, DedupTopK, Gallery, TopK, class_dedup_topk, cosine_topk,
                         top1_top3, top1_top3_dedup, topk_hits)
+from .store import (GalleryStore, GalleryWriter, StreamedGallery, block_ranges, gather_embeddings,
+                    write_gallery)
 from .sharded import PeerExchange, ShardedGallery, exchange_candidates, shard_bounds
 
 __all__ = [
@@ -20,5 +22,6 @@ __all__ = [
     "triplet_losses", "triplet_losses_fwd_bwd",
     "CosineSimilarity", "Gallery", "TopK", "DedupTopK", "cosine_topk", "top1_top3", "topk_hits",
     "class_dedup_topk", "top1_top3_dedup", "get_fm", "cross_entropy_pair", "CEPair",
-    "ShardedGallery", "PeerExchange", "CapturedSearch", "exchange_candidates", "shard_bounds",
+    "GalleryStore", "GalleryWriter", "StreamedGallery", "write_gallery", "gather_embeddings",
+    "block_ranges", "ShardedGallery", "PeerExchange", "CapturedSearch", "exchange_candidates", "shard_bounds",
 ]
