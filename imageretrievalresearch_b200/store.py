@@ -262,6 +262,8 @@ class StreamedGallery:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("StreamedGallery streams to a CUDA device (there is no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         if buffers < 2:
             raise ValueError("need at least two device buffers to overlap copy and search")
         self.store = source if isinstance(source, GalleryStore) else None

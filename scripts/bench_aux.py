@@ -182,6 +182,25 @@ def pool():
               flush=True)
 
 
+def streamed():
+    """Host-resident gallery scanned block by block (StreamedGallery): bound by the host link."""
+    N, D = 1_000_000, 1536
+    host = torch.randn(N, D).to(torch.bfloat16).pin_memory()
+    for Q, blk in ((64, 1 << 17), (4096, 1 << 17), (4096, 1 << 15)):
+        sg = irr.StreamedGallery(host, blk, "cuda", buffers=3)
+        q = torch.randn(Q, D, device="cuda", dtype=torch.bfloat16)
+        ms = timed(lambda i: sg.search(q, 3), 5, warm=2)
+        by = N * D * 2
+        print(json.dumps({"what": "streamed scan of a pinned host gallery 1M x 1536 bf16, top-3", "Q": Q,
+                          "block_rows": blk, "ms": ms, "host_link_GBps": by / ms / 1e6,
+                          "queries_per_s": Q / (ms * 1e-3)}), flush=True)
+    # plain pinned->device copy of the same bytes: the link's own ceiling on this box
+    dst = torch.empty(N, D, dtype=torch.bfloat16, device="cuda")
+    ms = timed(lambda i: dst.copy_(host, non_blocking=True), 5, warm=2)
+    print(json.dumps({"what": "cudaMemcpyAsync pinned->device of the same 3.07 GB", "ms": ms,
+                      "host_link_GBps": N * D * 2 / ms / 1e6}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["losses", "f32", "smallq"]
     for w in which:
