@@ -20,15 +20,18 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
             "(there is no CPU fallback)")
 
 
-def as_rows(t: torch.Tensor, name: str) -> torch.Tensor:
+def as_rows(t: torch.Tensor, name: str, keep_f16: bool = False) -> torch.Tensor:
     """[rows, D] contiguous fp32/bf16 CUDA tensor.  fp16 (autocast embeddings) is widened to fp32,
-    which is what the reference's autocast does for every reduction on this path."""
+    which is what the reference's autocast does for every reduction on this path —
+    except with ``keep_f16``: the row-norm / row-wise cosine kernels read fp16 directly (exact fp32
+    arithmetic on the fp16 values, no widening copy), and the search sends fp16 rows to the
+    tensor-core path when the caller opted in (``fp16_tensor_path``)."""
     _require_cuda(t, name)
     if t.dim() != 2:
         raise ValueError(f"{name} must be 2-D [rows, D], got shape {tuple(t.shape)}")
-    if t.dtype == torch.float16 or t.dtype == torch.float64:
+    if t.dtype == torch.float64 or (t.dtype == torch.float16 and not (keep_f16 and t.shape[1] % 8 == 0)):
         t = t.float()
-    if t.dtype not in (torch.float32, torch.bfloat16):
+    if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         raise TypeError(f"{name}: unsupported dtype {t.dtype}")
     t = t.detach()
     if not t.is_contiguous():
@@ -37,7 +40,17 @@ def as_rows(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def dtype_code(t: torch.Tensor) -> int:
-    return IRR_BF16 if t.dtype == torch.bfloat16 else IRR_F32
+    return {torch.bfloat16: IRR_BF16, torch.float16: _lib.IRR_F16}.get(t.dtype, IRR_F32)
+
+
+def same_kind(a: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp16 rows meeting fp32 rows: widen the fp16 side (what the reference's autocast does)."""
+    if a.dtype != b.dtype:
+        if a.dtype == torch.float16 and b.dtype == torch.float32:
+            a = a.float()
+        elif b.dtype == torch.float16 and a.dtype == torch.float32:
+            b = b.float()
+    return a, b
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -91,7 +104,7 @@ def check_same(a: torch.Tensor, b: torch.Tensor, an: str, bn: str) -> None:
 # -------------------------------------------------------------------------------------------------
 def row_inv_norms(x: torch.Tensor, eps: float) -> torch.Tensor:
     lib = _lib.load()
-    x = as_rows(x, "x")
+    x = as_rows(x, "x", keep_f16=True)
     out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         check(lib.irr_row_inv_norms(ptr(x), x.shape[0], x.shape[1], dtype_code(x), eps, ptr(out),

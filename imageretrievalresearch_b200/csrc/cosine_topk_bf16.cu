@@ -210,7 +210,8 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         int Q, int N, int num_kb, int k, int m_tiles, int n_tiles,
                         int tiles_per_chunk, int n_chunks, float* __restrict__ part_val,
                         int32_t* __restrict__ part_idx, float* __restrict__ scores_out,
-                        uint64_t g_policy, float eps, int a_rows, uint32_t* __restrict__ row_floor) {
+                        uint64_t g_policy, float eps, int a_rows, uint32_t* __restrict__ row_floor,
+                        int is_f16) {
   using G = SC<MT>;
   constexpr int STAGES = G::STAGES;
   constexpr int ACC = G::ACC;
@@ -295,7 +296,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    const uint32_t idesc = umma_idesc_16(BLOCK_M, BLOCK_N, is_f16 != 0);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t it = 0;  // accumulator tiles issued by this CTA
@@ -363,14 +364,14 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint32_t y0[4] = {w0.x, w0.y, w0.z, w0.w}, y1[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float a = bf16lo(x0[e]), c = bf16hi(x0[e]);
-              s0a = fmaf(a, a, s0a); s0a = fmaf(c, c, s0a);
-              a = bf16lo(x1[e]); c = bf16hi(x1[e]);
-              s0b = fmaf(a, a, s0b); s0b = fmaf(c, c, s0b);
-              a = bf16lo(y0[e]); c = bf16hi(y0[e]);
-              s1a = fmaf(a, a, s1a); s1a = fmaf(c, c, s1a);
-              a = bf16lo(y1[e]); c = bf16hi(y1[e]);
-              s1b = fmaf(a, a, s1b); s1b = fmaf(c, c, s1b);
+              float2 f = unpack16x2(x0[e], is_f16 != 0);
+              s0a = fmaf(f.x, f.x, s0a); s0a = fmaf(f.y, f.y, s0a);
+              f = unpack16x2(x1[e], is_f16 != 0);
+              s0b = fmaf(f.x, f.x, s0b); s0b = fmaf(f.y, f.y, s0b);
+              f = unpack16x2(y0[e], is_f16 != 0);
+              s1a = fmaf(f.x, f.x, s1a); s1a = fmaf(f.y, f.y, s1a);
+              f = unpack16x2(y1[e], is_f16 != 0);
+              s1b = fmaf(f.x, f.x, s1b); s1b = fmaf(f.y, f.y, s1b);
             }
           }
           __syncwarp();
@@ -489,7 +490,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                              const float* __restrict__ g_inv_norm, int Q, int N, int num_kb, int k,
                              int m_pairs, int n_tiles, int tiles_per_chunk, int n_chunks,
                              float* __restrict__ part_val, int32_t* __restrict__ part_idx,
-                             uint32_t* __restrict__ row_floor) {
+                             uint32_t* __restrict__ row_floor, int is_f16) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -562,7 +563,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N);
+      const uint32_t idesc = umma_idesc_16(2 * BLOCK_M, BLOCK_N, is_f16 != 0);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
@@ -700,14 +701,14 @@ bool use_pair(int64_t Q, bool cached_norms) {
 template <int KMAX>
 irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, int64_t Q,
                        int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
-                       uint32_t* row_floor, cudaStream_t st) {
+                       uint32_t* row_floor, bool f16, cudaStream_t st) {
   auto kern = cosine_topk_bf16_pair_kernel<KMAX>;
   IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
   const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
   profile_mark_start(st);
   kern<<<p.grid, P_THREADS, P_SMEM_ALLOC, st>>>(tq, tg, gin, static_cast<int>(Q), static_cast<int>(N),
                                                 num_kb, k, p.m_tiles, p.n_tiles, p.tiles_per_chunk,
-                                                p.n_chunks, pv, pi, row_floor);
+                                                p.n_chunks, pv, pi, row_floor, f16 ? 1 : 0);
   profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -731,16 +732,16 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// [rows, cols] bf16 row-major, tile = box_rows x 64 columns, 128-byte swizzle, zero fill OOB
+// [rows, cols] bf16 / fp16 row-major, tile = box_rows x 64 columns, 128-byte swizzle, zero fill OOB
 bool encode_bf16_rows(CUtensorMap* m, const void* base, int64_t rows, int64_t cols,
-                      uint32_t box_rows) {
+                      uint32_t box_rows, bool f16 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
   cuuint32_t box[2] = {BLOCK_K, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+  return fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -761,7 +762,7 @@ int tiles_per_unit(int64_t Q, bool cached_norms) {
 template <int KMAX, bool WS, bool FN, int MT = 1>
 irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, const float* qin,
                   int64_t Q, int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
-                  float* scores, float eps, uint32_t* row_floor, cudaStream_t st) {
+                  float* scores, float eps, uint32_t* row_floor, bool f16, cudaStream_t st) {
   auto kern = cosine_topk_bf16_kernel<KMAX, WS, FN, MT>;
   constexpr int SMEM_ALLOC = SC<MT>::ALLOC;
   IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
@@ -773,7 +774,8 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
   kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(tq, tg, gin, qin, static_cast<int>(Q),
                                                 static_cast<int>(N), num_kb, k, p.m_tiles,
                                                 p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
-                                                scores, g_policy, eps, a_box_rows(Q, MT), row_floor);
+                                                scores, g_policy, eps, a_box_rows(Q, MT), row_floor,
+                                                f16 ? 1 : 0);
   if (!WS) profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -798,8 +800,9 @@ size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
 irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
                             int64_t N, int32_t D, int32_t k, float eps, int64_t idx_offset,
                             float* out_val, int64_t* out_idx, void* ws, size_t ws_bytes,
-                            cudaStream_t st) {
+                            cudaStream_t st, irr_dtype dt) {
   if (device_cc() / 10 != 10) return IRR_ERR_UNSUPPORTED_DEVICE;
+  const bool f16 = dt == IRR_F16;
   if (N > 0x7fffff00ll || Q > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
   if (ws_bytes < bf16_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
   const bool cached = g_inv_norm != nullptr;
@@ -823,25 +826,25 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   const bool fuse = !cached && !pair && p.m_tiles == 1;
   const float* gin = g_inv_norm;
   if (!gin && !fuse) {
-    irr_status s = row_inv_norms(g, N, D, IRR_BF16, eps, gin_ws, st);
+    irr_status s = row_inv_norms(g, N, D, dt, eps, gin_ws, st);
     if (s != IRR_OK) return s;
     gin = gin_ws;
   }
   CUtensorMap tq, tg;
-  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q, mt)) ||
-      !encode_bf16_rows(&tg, g, N, D, pair ? P_B_ROWS : BLOCK_N))
+  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q, mt), f16) ||
+      !encode_bf16_rows(&tg, g, N, D, pair ? P_B_ROWS : BLOCK_N, f16))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   irr_status s;
   if (pair) {
     if (k <= 4)
-      s = launch_pair<4>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, st);
+      s = launch_pair<4>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, f16, st);
     else
-      s = launch_pair<16>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, st);
+      s = launch_pair<16>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, f16, st);
   } else {
     // (KMAX, fused norms, query tiles per unit) -> instantiation
 #define IRR_LAUNCH_SC(KM, FN, MTV)                                                              \
   s = launch<KM, false, FN, MTV>(tq, tg, FN ? nullptr : gin, nullptr, Q, N, D, k, p, pv, pi,    \
-                                 nullptr, eps, row_floor, st)
+                                 nullptr, eps, row_floor, f16, st)
     if (mt == 2) {  // only chosen without cached norms: always the fused-norm variant
       if (k <= 4) IRR_LAUNCH_SC(4, true, 2); else IRR_LAUNCH_SC(16, true, 2);
     } else {
@@ -851,8 +854,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
 #undef IRR_LAUNCH_SC
   }
   if (s != IRR_OK) return s;
-  return merge_partials(pv, pi, p.n_chunks, Q, k, q, D, IRR_BF16, eps, idx_offset, out_val, out_idx,
-                        st);
+  return merge_partials(pv, pi, p.n_chunks, Q, k, q, D, dt, eps, idx_offset, out_val, out_idx, st);
 }
 
 irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N, int32_t D,
@@ -873,20 +875,22 @@ irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N
   if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   return launch<4, true, false>(tq, tg, gin, qin, Q, N, D, 1, p, nullptr, nullptr, out_scores, eps,
-                                nullptr, st);
+                                nullptr, false, st);
 }
 
 // dense [Q,N] cosine scores with both inverse norms supplied (a block of the large-k path)
 irr_status bf16_scores_block(const void* q, const void* g, const float* g_inv_norm,
                              const float* q_inv_norm, int64_t Q, int64_t N, int32_t D, float eps,
-                             float* out_scores, cudaStream_t st) {
+                             float* out_scores, cudaStream_t st, irr_dtype dt) {
   if (device_cc() / 10 != 10) return IRR_ERR_UNSUPPORTED_DEVICE;
+  const bool f16 = dt == IRR_F16;
   const Plan p = make_plan(Q, N);
   CUtensorMap tq, tg;
-  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
+  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q), f16) ||
+      !encode_bf16_rows(&tg, g, N, D, BLOCK_N, f16))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   return launch<4, true, false>(tq, tg, g_inv_norm, q_inv_norm, Q, N, D, 1, p, nullptr, nullptr,
-                                out_scores, eps, nullptr, st);
+                                out_scores, eps, nullptr, f16, st);
 }
 
 }  // namespace irr

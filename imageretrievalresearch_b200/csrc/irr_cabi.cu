@@ -51,8 +51,11 @@ namespace {
 
 bool any_float(irr_dtype dt) { return dt == IRR_F32 || dt == IRR_BF16 || dt == IRR_F16; }
 
-irr_status check_rows(const void* p, int32_t D, irr_dtype dt) {
-  if (dt != IRR_F32 && dt != IRR_BF16) return IRR_ERR_UNSUPPORTED_DTYPE;
+// allow_f16: the search / similarity entry points take fp16 rows (autocast embeddings) on the
+// tensor-core path; the loss kernels do not
+irr_status check_rows(const void* p, int32_t D, irr_dtype dt, bool allow_f16 = false) {
+  if (dt != IRR_F32 && dt != IRR_BF16 && !(allow_f16 && dt == IRR_F16))
+    return IRR_ERR_UNSUPPORTED_DTYPE;
   if (D <= 0) return IRR_ERR_INVALID_ARG;
   if ((D * dtype_bytes(dt)) % 16 != 0) return IRR_ERR_ALIGNMENT;
   if (p && !aligned16(p)) return IRR_ERR_ALIGNMENT;
@@ -100,8 +103,8 @@ irr_status large_k_cosine_topk(const void* q, const void* g, const float* g_inv_
   for (int64_t b0 = 0; b0 < Q; b0 += qb) {
     const int64_t rows = b0 + qb <= Q ? qb : Q - b0;
     const void* qblk = static_cast<const uint8_t*>(q) + b0 * row_bytes;
-    if (dt == IRR_BF16)
-      s = bf16_scores_block(qblk, g, gin, qin + b0, rows, N, D, eps, scores, st);
+    if (dt != IRR_F32)
+      s = bf16_scores_block(qblk, g, gin, qin + b0, rows, N, D, eps, scores, st, dt);
     else
       s = f32_cosine_scores(qblk, g, gin, qin + b0, rows, N, D, scores, st);
     if (s != IRR_OK) return s;
@@ -143,7 +146,7 @@ size_t irr_cosine_topk_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t 
   (void)D;
   if (Q < 0 || N < 0 || k < 1) return 0;
   if (k > IRR_MAX_K_FUSED) return large_k_workspace_bytes(Q, N);
-  return dt == IRR_BF16 ? bf16_topk_workspace_bytes(Q, N, k) : f32_topk_workspace_bytes(Q, N, k);
+  return dt != IRR_F32 ? bf16_topk_workspace_bytes(Q, N, k) : f32_topk_workspace_bytes(Q, N, k);
 }
 
 irr_status irr_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
@@ -154,17 +157,17 @@ irr_status irr_cosine_topk(const void* q, const void* g, const float* g_inv_norm
   if (k > IRR_MAX_K) return IRR_ERR_K_TOO_LARGE;
   if (Q == 0) return IRR_OK;
   if (!q || (N > 0 && !g) || !workspace) return IRR_ERR_INVALID_ARG;
-  irr_status s = check_rows(q, D, dt);
+  irr_status s = check_rows(q, D, dt, true);
   if (s != IRR_OK) return s;
-  s = check_rows(g, D, dt);
+  s = check_rows(g, D, dt, true);
   if (s != IRR_OK) return s;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (k > IRR_MAX_K_FUSED)
     return large_k_cosine_topk(q, g, g_inv_norm, Q, N, D, k, dt, eps, idx_offset, out_val, out_idx,
                                workspace, workspace_bytes, st);
-  if (dt == IRR_BF16)
+  if (dt != IRR_F32)
     return bf16_cosine_topk(q, g, g_inv_norm, Q, N, D, k, eps, idx_offset, out_val, out_idx,
-                            workspace, workspace_bytes, st);
+                            workspace, workspace_bytes, st, dt);
   return f32_cosine_topk(q, g, g_inv_norm, Q, N, D, k, eps, idx_offset, out_val, out_idx, workspace,
                          workspace_bytes, st);
 }
@@ -184,7 +187,7 @@ irr_status irr_cosine_scores_bf16(const void* q, const void* g, int64_t Q, int64
 irr_status irr_row_inv_norms(const void* x, int64_t N, int32_t D, irr_dtype dt, float eps,
                              float* out, irr_stream_t stream) {
   if (N < 0 || (N > 0 && (!x || !out))) return IRR_ERR_INVALID_ARG;
-  irr_status s = check_rows(x, D, dt);
+  irr_status s = check_rows(x, D, dt, true);
   if (s != IRR_OK) return s;
   return row_inv_norms(x, N, D, dt, eps, out, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -317,9 +320,9 @@ irr_status irr_pair_cosine(const void* x1, int64_t x1_rows, const void* x2, int6
                            irr_dtype dt, float eps, float* out, irr_stream_t stream) {
   if (N < 0 || (x1_rows != N && x1_rows != 1)) return IRR_ERR_INVALID_ARG;
   if (N > 0 && (!x1 || !x2 || !out)) return IRR_ERR_INVALID_ARG;
-  irr_status s = check_rows(x1, D, dt);
+  irr_status s = check_rows(x1, D, dt, true);
   if (s != IRR_OK) return s;
-  s = check_rows(x2, D, dt);
+  s = check_rows(x2, D, dt, true);
   if (s != IRR_OK) return s;
   return pair_cosine(x1, x1_rows, x2, N, D, dt, eps, out, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -5,6 +5,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -35,7 +36,7 @@ constexpr float kContrastiveEps = 1e-9f;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-inline int dtype_bytes(irr_dtype dt) { return dt == IRR_BF16 ? 2 : 4; }
+inline int dtype_bytes(irr_dtype dt) { return dt == IRR_F32 ? 4 : 2; }
 
 // Number of SMs of the current device (148 on B200); 148 when no device is visible so that the
 // workspace-size queries stay callable on a CPU-only build box.
@@ -79,6 +80,15 @@ __device__ __forceinline__ bool elect_one() {
 // two packed bf16 (one 32-bit word) -> two fp32, exact
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// two packed fp16 (one 32-bit word) -> two fp32, exact
+__device__ __forceinline__ float2 f16x2(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+// two packed 16-bit floats of either kind; `f16` is warp-uniform
+__device__ __forceinline__ float2 unpack16x2(uint32_t w, bool f16) {
+  return f16 ? f16x2(w) : make_float2(bf16lo(w), bf16hi(w));
+}
 
 // 128-bit streaming global load (read once: do not allocate in L1)
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
@@ -333,6 +343,11 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;                         // version = 1
   d |= static_cast<uint64_t>(2) << 61;                         // SWIZZLE_128B
   return d;
+}
+// instruction descriptor, kind::f16: D=f32, A=B=fp16 (format 0) or bf16 (format 1), both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, bool f16) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 // instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, shape M x N
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {

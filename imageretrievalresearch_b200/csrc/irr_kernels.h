@@ -45,14 +45,14 @@ size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k);
 irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
                             int64_t N, int32_t D, int32_t k, float eps, int64_t idx_offset,
                             float* out_val, int64_t* out_idx, void* ws, size_t ws_bytes,
-                            cudaStream_t st);
+                            cudaStream_t st, irr_dtype dt = IRR_BF16 /* or IRR_F16 */);
 irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N, int32_t D,
                               float eps, float* out_scores, void* ws, size_t ws_bytes,
                               cudaStream_t st);
 
 irr_status bf16_scores_block(const void* q, const void* g, const float* g_inv_norm,
                              const float* q_inv_norm, int64_t Q, int64_t N, int32_t D, float eps,
-                             float* out_scores, cudaStream_t st);
+                             float* out_scores, cudaStream_t st, irr_dtype dt = IRR_BF16);
 
 // topk_select.cu (large k: select from a dense score block; class de-duplication)
 irr_status topk_select(const float* scores, int64_t Q, int64_t N, int32_t k, int64_t idx_offset,

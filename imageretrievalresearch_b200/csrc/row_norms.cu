@@ -13,16 +13,17 @@ namespace {
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 
-template <bool BF16>
+// ELT: element kind of the rows = irr_dtype (0 fp32, 1 bf16, 2 fp16)
+template <int ELT>
 __device__ __forceinline__ float sumsq_vec(const uint4& u) {
-  if (BF16) {
+  if (ELT != IRR_F32) {
     float s = 0.f;
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float a = bf16lo(w[j]), b = bf16hi(w[j]);
-      s = fmaf(a, a, s);
-      s = fmaf(b, b, s);
+      const float2 f = unpack16x2(w[j], ELT == IRR_F16);
+      s = fmaf(f.x, f.x, s);
+      s = fmaf(f.y, f.y, s);
     }
     return s;
   } else {
@@ -32,16 +33,16 @@ __device__ __forceinline__ float sumsq_vec(const uint4& u) {
   }
 }
 
-template <bool BF16>
+template <int ELT>
 __device__ __forceinline__ void dot3_vec(const uint4& ua, const uint4& ub, float& aa, float& bb,
                                          float& ab) {
-  if (BF16) {
+  if (ELT != IRR_F32) {
     const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w};
     const uint32_t wb[4] = {ub.x, ub.y, ub.z, ub.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float a0 = bf16lo(wa[j]), a1 = bf16hi(wa[j]);
-      const float b0 = bf16lo(wb[j]), b1 = bf16hi(wb[j]);
+      const float2 fa = unpack16x2(wa[j], ELT == IRR_F16), fb = unpack16x2(wb[j], ELT == IRR_F16);
+      const float a0 = fa.x, a1 = fa.y, b0 = fb.x, b1 = fb.y;
       aa = fmaf(a0, a0, fmaf(a1, a1, aa));
       bb = fmaf(b0, b0, fmaf(b1, b1, bb));
       ab = fmaf(a0, b0, fmaf(a1, b1, ab));
@@ -60,7 +61,7 @@ __device__ __forceinline__ void dot3_vec(const uint4& ua, const uint4& ub, float
   }
 }
 
-template <bool BF16>
+template <int ELT>
 __global__ void __launch_bounds__(THREADS)
 row_inv_norm_kernel(const uint4* __restrict__ x, int64_t N, int vec_per_row, float eps,
                     float* __restrict__ out) {
@@ -74,18 +75,18 @@ row_inv_norm_kernel(const uint4* __restrict__ x, int64_t N, int vec_per_row, flo
     for (; v + 96 < vec_per_row; v += 128) {
       const uint4 u0 = ldg_stream(r + v), u1 = ldg_stream(r + v + 32), u2 = ldg_stream(r + v + 64),
                   u3 = ldg_stream(r + v + 96);
-      s0 += sumsq_vec<BF16>(u0);
-      s1 += sumsq_vec<BF16>(u1);
-      s2 += sumsq_vec<BF16>(u2);
-      s3 += sumsq_vec<BF16>(u3);
+      s0 += sumsq_vec<ELT>(u0);
+      s1 += sumsq_vec<ELT>(u1);
+      s2 += sumsq_vec<ELT>(u2);
+      s3 += sumsq_vec<ELT>(u3);
     }
-    for (; v < vec_per_row; v += 32) s0 += sumsq_vec<BF16>(ldg_stream(r + v));
+    for (; v < vec_per_row; v += 32) s0 += sumsq_vec<ELT>(ldg_stream(r + v));
     const float ss = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) out[row] = 1.0f / fmaxf(sqrtf(ss), eps);
   }
 }
 
-template <bool BF16>
+template <int ELT>
 __global__ void __launch_bounds__(THREADS)
 pair_cosine_kernel(const uint4* __restrict__ x1, int64_t x1_row_stride_vec,
                    const uint4* __restrict__ x2, int64_t N, int vec_per_row, float eps,
@@ -101,10 +102,10 @@ pair_cosine_kernel(const uint4* __restrict__ x1, int64_t x1_row_stride_vec,
     for (; v + 32 < vec_per_row; v += 64) {
       const uint4 a0 = __ldg(a + v), a1 = __ldg(a + v + 32);
       const uint4 b0 = ldg_stream(b + v), b1 = ldg_stream(b + v + 32);
-      dot3_vec<BF16>(a0, b0, aa, bb, ab);
-      dot3_vec<BF16>(a1, b1, aa, bb, ab);
+      dot3_vec<ELT>(a0, b0, aa, bb, ab);
+      dot3_vec<ELT>(a1, b1, aa, bb, ab);
     }
-    for (; v < vec_per_row; v += 32) dot3_vec<BF16>(__ldg(a + v), ldg_stream(b + v), aa, bb, ab);
+    for (; v < vec_per_row; v += 32) dot3_vec<ELT>(__ldg(a + v), ldg_stream(b + v), aa, bb, ab);
     aa = warp_sum(aa);
     bb = warp_sum(bb);
     ab = warp_sum(ab);
@@ -125,10 +126,13 @@ irr_status row_inv_norms(const void* x, int64_t N, int32_t D, irr_dtype dt, floa
   if (N == 0) return IRR_OK;
   const int vec = D * dtype_bytes(dt) / 16;
   const int grid = grid_for_rows(N);
+  const uint4* xv = static_cast<const uint4*>(x);
   if (dt == IRR_BF16)
-    row_inv_norm_kernel<true><<<grid, THREADS, 0, st>>>(static_cast<const uint4*>(x), N, vec, eps, out);
+    row_inv_norm_kernel<IRR_BF16><<<grid, THREADS, 0, st>>>(xv, N, vec, eps, out);
+  else if (dt == IRR_F16)
+    row_inv_norm_kernel<IRR_F16><<<grid, THREADS, 0, st>>>(xv, N, vec, eps, out);
   else
-    row_inv_norm_kernel<false><<<grid, THREADS, 0, st>>>(static_cast<const uint4*>(x), N, vec, eps, out);
+    row_inv_norm_kernel<IRR_F32><<<grid, THREADS, 0, st>>>(xv, N, vec, eps, out);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
 }
@@ -139,12 +143,13 @@ irr_status pair_cosine(const void* x1, int64_t x1_rows, const void* x2, int64_t 
   const int vec = D * dtype_bytes(dt) / 16;
   const int64_t s1 = x1_rows == 1 ? 0 : vec;
   const int grid = grid_for_rows(N);
+  const uint4 *a = static_cast<const uint4*>(x1), *b = static_cast<const uint4*>(x2);
   if (dt == IRR_BF16)
-    pair_cosine_kernel<true><<<grid, THREADS, 0, st>>>(static_cast<const uint4*>(x1), s1,
-                                                       static_cast<const uint4*>(x2), N, vec, eps, out);
+    pair_cosine_kernel<IRR_BF16><<<grid, THREADS, 0, st>>>(a, s1, b, N, vec, eps, out);
+  else if (dt == IRR_F16)
+    pair_cosine_kernel<IRR_F16><<<grid, THREADS, 0, st>>>(a, s1, b, N, vec, eps, out);
   else
-    pair_cosine_kernel<false><<<grid, THREADS, 0, st>>>(static_cast<const uint4*>(x1), s1,
-                                                        static_cast<const uint4*>(x2), N, vec, eps, out);
+    pair_cosine_kernel<IRR_F32><<<grid, THREADS, 0, st>>>(a, s1, b, N, vec, eps, out);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
 }

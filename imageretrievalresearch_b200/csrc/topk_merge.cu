@@ -20,7 +20,7 @@ constexpr int WARPS = THREADS / 32;
 template <int KMAX>
 __global__ void __launch_bounds__(THREADS)
 merge_partials_kernel(const float* __restrict__ part_val, const int32_t* __restrict__ part_idx,
-                      int S, int64_t Q, int k, const void* __restrict__ q, int D, int is_bf16,
+                      int S, int64_t Q, int k, const void* __restrict__ q, int D, int elt,
                       float eps, int64_t idx_offset, float* __restrict__ out_val,
                       int64_t* __restrict__ out_idx) {
   const int lane = threadIdx.x & 31;
@@ -29,12 +29,11 @@ merge_partials_kernel(const float* __restrict__ part_val, const int32_t* __restr
 
   // query norm
   float ss = 0.f;
-  if (is_bf16) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(q) + qi * D);
+  if (elt != IRR_F32) {   // bf16 / fp16 rows: two elements per 32-bit word
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(static_cast<const uint16_t*>(q) + qi * D);
     for (int v = lane; v < D / 2; v += 32) {
-      const uint32_t w = __ldg(r + v);
-      const float a = bf16lo(w), b = bf16hi(w);
-      ss = fmaf(a, a, fmaf(b, b, ss));
+      const float2 f = unpack16x2(__ldg(r + v), elt == IRR_F16);
+      ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
     }
   } else {
     const float* r = static_cast<const float*>(q) + qi * D;
@@ -127,10 +126,10 @@ irr_status merge_partials(const float* part_val, const int32_t* part_idx, int32_
   const int grid = static_cast<int>((Q + WARPS - 1) / WARPS);
   if (k <= 4)
     merge_partials_kernel<4><<<grid, THREADS, 0, st>>>(part_val, part_idx, S, Q, k, q, D,
-                                                       dt == IRR_BF16, eps, idx_offset, out_val, out_idx);
+                                                       static_cast<int>(dt), eps, idx_offset, out_val, out_idx);
   else
     merge_partials_kernel<16><<<grid, THREADS, 0, st>>>(part_val, part_idx, S, Q, k, q, D,
-                                                        dt == IRR_BF16, eps, idx_offset, out_val, out_idx);
+                                                        static_cast<int>(dt), eps, idx_offset, out_val, out_idx);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
 }

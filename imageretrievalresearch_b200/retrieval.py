@@ -44,7 +44,8 @@ class CosineSimilarity(torch.nn.Module):
             x2 = x2.unsqueeze(0)
         if x2.shape[0] == 1 and x1.shape[0] != 1:
             x1, x2 = x2, x1  # cosine is symmetric
-        a, b = _ops.as_rows(x1, "x1"), _ops.as_rows(x2, "x2")
+        a, b = _ops.same_kind(_ops.as_rows(x1, "x1", keep_f16=True),
+                              _ops.as_rows(x2, "x2", keep_f16=True))
         _ops.check_same(a, b, "x1", "x2")
         if a.shape[0] not in (1, b.shape[0]):
             raise RuntimeError(
@@ -56,13 +57,18 @@ class CosineSimilarity(torch.nn.Module):
 def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, eps: float = 1e-6, *,
                 gallery_inv_norm: Optional[torch.Tensor] = None, idx_offset: int = 0,
                 allow_short: bool = False,
-                out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> TopK:
+                out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                fp16_tensor_path: bool = False) -> TopK:
     """Fused ``topk(cos(q_i[None], gallery), k)`` for every query row.
 
     Row ``i`` of the result is what the reference's per-query loop yields for query ``i``:
     values sorted descending, int64 indices; ties resolve to the lower gallery index (torch.topk
-    leaves tie order unspecified).  fp32 inputs take the exact FFMA path, bf16 inputs the
-    tcgen05 tensor-core path; both accumulate and emit fp32.  The Q x N score matrix is never
+    leaves tie order unspecified).  fp32 inputs take the exact FFMA path, bf16 inputs the tcgen05
+    tensor-core path; both accumulate and emit fp32.  fp16 inputs (what the reference's
+    ``precision=16`` training produces) are widened to fp32 like the reference's autocast does —
+    unless ``fp16_tensor_path=True``, which sends them to the tensor cores as fp16 (kind::f16):
+    same ranking rule, scores within ~2e-5 of the fp32 result (tensor-core accumulation truncates;
+    measured 1.0e-5 at D=1920), i.e. outside the fp32-mode bar of 1e-5 relative, hence opt-in.  The Q x N score matrix is never
     materialised.
 
     gallery_inv_norm: cached ``1/max(|g|, eps)`` per gallery row (see :class:`Gallery`).
@@ -70,7 +76,8 @@ def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, eps: float
     allow_short: a shard with fewer than ``k`` rows pads with (-inf, -1) instead of raising.
     out: optional preallocated contiguous (values fp32 [Q,k], indices int64 [Q,k]) to write into.
     """
-    q, g = _ops.as_rows(queries, "queries"), _ops.as_rows(gallery, "gallery")
+    q, g = _ops.same_kind(_ops.as_rows(queries, "queries", keep_f16=fp16_tensor_path),
+                          _ops.as_rows(gallery, "gallery", keep_f16=fp16_tensor_path))
     _ops.check_same(q, g, "queries", "gallery")
     if not isinstance(k, int) or k < 1:
         raise ValueError(f"k must be a positive int, got {k!r}")
@@ -161,8 +168,9 @@ class Gallery:
     """
 
     def __init__(self, embeddings: torch.Tensor, eps: float = 1e-6, first_row: int = 0,
-                 cache_norms: bool = True) -> None:
-        self.embeddings = _ops.as_rows(embeddings, "embeddings")
+                 cache_norms: bool = True, fp16_tensor_path: bool = False) -> None:
+        self.fp16_tensor_path = fp16_tensor_path
+        self.embeddings = _ops.as_rows(embeddings, "embeddings", keep_f16=fp16_tensor_path)
         self.eps = eps
         self.first_row = int(first_row)
         self.inv_norm = _ops.row_inv_norms(self.embeddings, eps) if cache_norms else None
@@ -174,7 +182,8 @@ class Gallery:
     def search(self, queries: torch.Tensor, k: int, allow_short: bool = False,
                out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> TopK:
         return cosine_topk(queries, self.embeddings, k, self.eps, gallery_inv_norm=self.inv_norm,
-                           idx_offset=self.first_row, allow_short=allow_short, out=out)
+                           idx_offset=self.first_row, allow_short=allow_short, out=out,
+                           fp16_tensor_path=self.fp16_tensor_path)
 
     def capture(self, num_queries: int, k: int) -> "CapturedSearch":
         """Record ``search`` for a fixed batch shape as a CUDA graph (see CapturedSearch)."""

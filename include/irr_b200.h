@@ -18,7 +18,7 @@
  *     the loss entry points start with self-resetting sync words: the buffer must be zero-filled
  *     ONCE before its first use and may then be reused by any number of calls on one stream.
  *   - row-major contiguous embeddings, row stride == D elements; base pointers 16-byte aligned;
- *     D % 8 == 0 for IRR_BF16 and D % 4 == 0 for IRR_F32 (1536 / 1920 / 2560 in the reference).
+ *     D % 8 == 0 for IRR_BF16 / IRR_F16 and D % 4 == 0 for IRR_F32 (1536 / 1920 / 2560 in the reference).
  *   - re-entrant and thread-safe for distinct streams + workspaces.
  *   - there is no CPU fallback: a device that is not sm_100 makes the bf16 tensor path return
  *     IRR_ERR_UNSUPPORTED_DEVICE.
@@ -54,7 +54,10 @@ enum {
   IRR_ERR_ROW_TOO_LONG = -7        /* D too large for the shared-memory staged loss kernels */
 };
 
-/* IRR_F16 is accepted only where stated (feature maps and logits produced under fp16 autocast) */
+/* IRR_F16 is accepted only where stated: feature maps and logits produced under fp16 autocast, and
+ * the rows of irr_cosine_topk / irr_cosine_topk_sharded / irr_row_inv_norms / irr_pair_cosine (the
+ * embeddings the reference's precision=16 training produces,
+ * train/train_efficient_cos_con_ce_loss.py:465) */
 typedef enum { IRR_F32 = 0, IRR_BF16 = 1, IRR_F16 = 2 } irr_dtype;
 
 /* largest k of irr_cosine_topk; up to IRR_MAX_K_FUSED the register-resident epilogues select inside
@@ -83,7 +86,8 @@ IRR_API const char* irr_status_string(irr_status s);
  *   inference/inference.py:169,235,240      inference/training_analysis.ipynb:187,238
  * with cos = CosineSimilarity(dim=1, eps): x1.x2 / (max(|x1|,eps) * max(|x2|,eps)).
  *
- * q [Q,D], g [N,D] of dtype `dt`; accumulate and emit fp32.
+ * q [Q,D], g [N,D] of dtype `dt` (F32: FFMA path; BF16 / F16: tcgen05 kind::f16 tensor path);
+ * accumulate and emit fp32.
  * g_inv_norm: optional device fp32[N] holding 1/max(|g_row|,eps) (cached by a gallery handle);
  *             NULL = computed inside the call.
  * out_val [Q,k] fp32 sorted descending, ties broken by LOWER gallery index;

@@ -183,6 +183,33 @@ def test_fp16_autocast_embeddings_are_widened():
     assert ((got - want).abs() <= LOSS_REL * want.abs() + 1e-8).all()
 
 
+@pytest.mark.parametrize("Q,N,D,k", [(64, 10_000, 1536, 3), (1, 257, 200, 3), (300, 5000, 1920, 10),
+                                     (640, 3000, 64, 1), (37, 4000, 256, 150)])
+def test_fp16_embeddings_on_the_tensor_path(Q, N, D, k):
+    """fp16 rows (what precision=16 training produces, train_efficient_cos_con_ce_loss.py:465):
+    by default widened to fp32 (exact path, fp32-mode bar); with fp16_tensor_path=True they run on
+    the tcgen05 kind::f16 path as fp16 and must match the reference's fp32 cosine_similarity on the
+    same fp16-valued inputs within 1e-4 absolute (tensor-core accumulation; bf16 mode allows 2e-2)."""
+    q, gal = synthetic.tied_gallery(N, D, Q, dtype=torch.float16)
+    exact = irr.cosine_topk(q.cuda(), gal.cuda(), min(k, 16))
+    check_topk(exact, q.float(), gal.float(), min(k, 16), FP32_REL, relative=True)
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), k, fp16_tensor_path=True)
+    check_topk(res, q.float(), gal.float(), k, 1e-4, relative=False)
+    assert res.values.dtype == torch.float32
+    cached = irr.Gallery(gal.cuda(), fp16_tensor_path=True).search(q.cuda(), k)
+    assert torch.equal(cached.indices, res.indices)
+    assert (cached.values - res.values).abs().max() < 1e-6
+    # ties (duplicated rows) resolve to the lower index on this path too
+    if k >= 2 and Q <= N // 2:
+        assert (res.indices[:, 0] < res.indices[:, 1]).all() and (res.values[:, 0] == res.values[:, 1]).all()
+    # row-wise similarity and mixed fp16 / fp32 operands (the fp16 side is widened)
+    cs = irr.CosineSimilarity(dim=1, eps=1e-6)
+    want = torch.nn.functional.cosine_similarity(q[:1].float(), gal.float(), dim=1, eps=1e-6)
+    assert (cs(q[:1].cuda(), gal.cuda()).cpu() - want).abs().max() < 2e-6
+    mixed = irr.cosine_topk(q.cuda().float(), gal.cuda(), min(k, 16))
+    check_topk(mixed, q.float(), gal.float(), min(k, 16), FP32_REL, relative=True)
+
+
 # -------------------------------------------------------------------------------------------------
 # edge cases: ragged shapes, ties, zero rows, short shards, k range, errors
 # -------------------------------------------------------------------------------------------------
