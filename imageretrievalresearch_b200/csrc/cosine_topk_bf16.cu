@@ -482,15 +482,57 @@ constexpr int P_SMEM_BARS = (2 * P_STAGES + 2 * ACC_STAGES) * 8;
 constexpr int P_SMEM_TOTAL = P_SMEM_TILES + SMEM_GN + P_SMEM_BARS + 16;
 constexpr int P_SMEM_ALLOC = P_SMEM_TOTAL + 1024;
 constexpr int P_THREADS = 256;
+constexpr int P_NORM_WARP0 = 8;            // NORMS_INSIDE: warps 8-11 produce the gallery norms
+constexpr int P_THREADS_NORM = 384;
+constexpr int OCTET = 8;                   // rows a norm warp finishes between two publications
+constexpr int OCTETS_PER_TILE = BLOCK_N / OCTET;
 
-template <int KMAX>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+// 128-bit streaming load that also leaves L2 first (the norm producers run far ahead of the tile
+// stream: what they touch must not displace the query tiles and the tiles in flight)
+__device__ __forceinline__ uint4 ldg_stream_evict_first(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(kPolicyEvictFirst));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+static __device__ __noinline__ void wait_tile_norms_slow(const uint32_t* cnt, uint32_t need, int tile) {
+  const uint64_t t0 = global_timer_ns();
+  while (ld_acquire_gpu(cnt) < need) {
+    if (global_timer_ns() - t0 > 4000000000ull) {
+      printf("irr_b200: norm watchdog: block %d tile %d has %u of %u rows\n", (int)blockIdx.x, tile,
+             ld_acquire_gpu(cnt), need);
+      __trap();
+    }
+    __nanosleep(100);
+  }
+}
+
+// NORMS_INSIDE (no cached norms): instead of a streaming pre-pass kernel, four extra warps per CTA
+// compute 1/max(|g|,eps) for the WHOLE gallery cooperatively across the grid, straight from global
+// memory, in the order the tile stream will need the tiles (the chunks that start together are
+// interleaved tile by tile), publish each finished octet of rows on a per-tile counter (fence +
+// atomic), and are done after about the time the pre-pass used to take — but concurrently with the
+// MMAs, which leave most of the DRAM bandwidth idle.  The epilogue waits (acquire) for its tile's
+// counter, which after the first few tiles is always complete already.  Every CTA is co-resident
+// (persistent grid) and producers wait for nothing, so the waits cannot deadlock; they trap on a
+// 4 s watchdog like the mbarriers.  Measured: neutral at Q=4096 (the chip is at its power cap: the
+// same joules take the same time wherever they are spent), a clear win for 257..2048 queries.
+template <int KMAX, bool NORMS_INSIDE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NORMS_INSIDE ? P_THREADS_NORM : P_THREADS, 1)
 cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                              const __grid_constant__ CUtensorMap tmap_g,
                              const float* __restrict__ g_inv_norm, int Q, int N, int num_kb, int k,
                              int m_pairs, int n_tiles, int tiles_per_chunk, int n_chunks,
                              float* __restrict__ part_val, int32_t* __restrict__ part_idx,
-                             uint32_t* __restrict__ row_floor, int is_f16) {
+                             uint32_t* __restrict__ row_floor, int is_f16,
+                             const uint4* __restrict__ g_rows, int vec_per_row, float eps,
+                             float* __restrict__ norm_out, uint32_t* __restrict__ tile_rows_done) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -596,7 +638,88 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else if (NORMS_INSIDE && warp >= P_NORM_WARP0) {
+    // ===================== gallery-norm producers (whole grid, need order) =====================
+    const int nw = static_cast<int>(blockIdx.x) * 4 + (warp - P_NORM_WARP0);
+    const int NW = static_cast<int>(gridDim.x) * 4;
+    const int group = (num_clusters + m_pairs - 1) / m_pairs;      // chunks that start together
+    const long long slots_per_group = 1ll * tiles_per_chunk * group * OCTETS_PER_TILE;
+    const long long total_slots = slots_per_group * ((n_chunks + group - 1) / group);
+    const bool f16 = is_f16 != 0;
+    for (long long o = nw; o < total_slots; o += NW) {
+      const int grp = static_cast<int>(o / slots_per_group);
+      const int rem = static_cast<int>(o - grp * slots_per_group);
+      const int j = rem / (group * OCTETS_PER_TILE);
+      const int r2 = rem - j * (group * OCTETS_PER_TILE);
+      const int chunk = grp * group + r2 / OCTETS_PER_TILE;
+      const int oct = r2 % OCTETS_PER_TILE;
+      if (chunk >= n_chunks) continue;
+      const int tile = chunk * tiles_per_chunk + j;
+      if (tile >= n_tiles || tile >= (chunk + 1) * tiles_per_chunk) continue;
+      const int row0 = tile * BLOCK_N + oct * OCTET;
+      if (row0 >= N) continue;
+      const int rows = min(OCTET, N - row0);
+      // four rows at a time, four 16-byte vectors per row and lane in flight (16 independent loads
+      // per lane = 8 KB per warp): the producers have to keep pace with the tile stream, which for a
+      // few hundred queries consumes the gallery at several TB/s
+      for (int r = 0; r < rows; r += 4) {
+        const uint4* base = g_rows + static_cast<size_t>(row0 + r) * vec_per_row;
+        const int nr = min(4, rows - r);
+        float ss[4] = {0.f, 0.f, 0.f, 0.f};
+        int v = lane;
+        for (; v + 96 < vec_per_row; v += 128) {
+          uint4 u[4][4];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              u[rr][c] = rr < nr ? ldg_stream_evict_first(base + rr * vec_per_row + v + 32 * c)
+                                 : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t w[4] = {u[rr][c].x, u[rr][c].y, u[rr][c].z, u[rr][c].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack16x2(w[e], f16);
+                ss[rr] = fmaf(f.x, f.x, ss[rr]);
+                ss[rr] = fmaf(f.y, f.y, ss[rr]);
+              }
+            }
+          }
+        }
+        for (; v < vec_per_row; v += 32) {
+          uint4 u[4];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr)
+            u[rr] = rr < nr ? ldg_stream_evict_first(base + rr * vec_per_row + v) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const uint32_t w[4] = {u[rr].x, u[rr].y, u[rr].z, u[rr].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack16x2(w[e], f16);
+              ss[rr] = fmaf(f.x, f.x, ss[rr]);
+              ss[rr] = fmaf(f.y, f.y, ss[rr]);
+            }
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) ss[rr] = warp_sum(ss[rr]);
+        if (lane < nr) {
+          const float mine = lane == 0 ? ss[0] : lane == 1 ? ss[1] : lane == 2 ? ss[2] : ss[3];
+          norm_out[row0 + r + lane] = 1.0f / fmaxf(sqrtf(mine), eps);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();                                  // the octet's norms before its count
+        atomicAdd(tile_rows_done + tile, static_cast<uint32_t>(rows));
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < P_NORM_WARP0) {
     // ===================== epilogue (both CTAs: own 128 query rows x 256 columns) ==========
     const int ew = warp - EPI_WARP0;
     const int et = threadIdx.x - EPI_WARP0 * 32;
@@ -617,8 +740,19 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         float* gn = gn_smem + as * BLOCK_N;
         {
           const int c0 = n0 + et, c1 = n0 + et + EPI_THREADS;
-          gn[et] = c0 < N ? __ldg(g_inv_norm + c0) : 0.0f;
-          gn[et + EPI_THREADS] = c1 < N ? __ldg(g_inv_norm + c1) : 0.0f;
+          if (NORMS_INSIDE) {
+            // producers publish rows in octets; the tile is usable once all of its rows are counted
+            if (lane == 0) {
+              const uint32_t need = static_cast<uint32_t>(min(BLOCK_N, N - n0));
+              if (ld_acquire_gpu(tile_rows_done + t) < need) wait_tile_norms_slow(tile_rows_done + t, need, t);
+            }
+            __syncwarp();
+            gn[et] = c0 < N ? __ldcg(g_inv_norm + c0) : 0.0f;
+            gn[et + EPI_THREADS] = c1 < N ? __ldcg(g_inv_norm + c1) : 0.0f;
+          } else {
+            gn[et] = c0 < N ? __ldg(g_inv_norm + c0) : 0.0f;
+            gn[et + EPI_THREADS] = c1 < N ? __ldg(g_inv_norm + c1) : 0.0f;
+          }
         }
         named_bar_sync(1, EPI_THREADS);
         mbar_wait(tfull_bar(as), aphase, 1400 + as);
@@ -698,17 +832,21 @@ bool use_pair(int64_t Q, bool cached_norms) {
   return Q > 3 * BLOCK_M;
 }
 
-template <int KMAX>
+// norms_inside: gin is the (not yet filled) fp32[N] buffer the in-kernel producers write and the
+// epilogues read; tile_done is the zeroed per-tile row counter array
+template <int KMAX, bool NORMS_INSIDE>
 irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, int64_t Q,
                        int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
-                       uint32_t* row_floor, bool f16, cudaStream_t st) {
-  auto kern = cosine_topk_bf16_pair_kernel<KMAX>;
+                       uint32_t* row_floor, bool f16, const void* g, float eps, uint32_t* tile_done,
+                       cudaStream_t st) {
+  auto kern = cosine_topk_bf16_pair_kernel<KMAX, NORMS_INSIDE>;
   IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
   const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
   profile_mark_start(st);
-  kern<<<p.grid, P_THREADS, P_SMEM_ALLOC, st>>>(tq, tg, gin, static_cast<int>(Q), static_cast<int>(N),
-                                                num_kb, k, p.m_tiles, p.n_tiles, p.tiles_per_chunk,
-                                                p.n_chunks, pv, pi, row_floor, f16 ? 1 : 0);
+  kern<<<p.grid, NORMS_INSIDE ? P_THREADS_NORM : P_THREADS, P_SMEM_ALLOC, st>>>(
+      tq, tg, gin, static_cast<int>(Q), static_cast<int>(N), num_kb, k, p.m_tiles, p.n_tiles,
+      p.tiles_per_chunk, p.n_chunks, pv, pi, row_floor, f16 ? 1 : 0, static_cast<const uint4*>(g),
+      D * 2 / 16, eps, const_cast<float*>(gin), tile_done);
   profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -783,7 +921,8 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
 
 }  // namespace
 
-// workspace: [g_inv_norm fp32 N][part_val fp32 chunks*Q*k][part_idx i32 chunks*Q*k][row_floor u32 Q]
+// workspace: [g_inv_norm fp32 N][part_val fp32 chunks*Q*k][part_idx i32 chunks*Q*k]
+//            [row_floor u32 Q | tile_rows_done u32 n_tiles]   (the last two are zeroed per call)
 size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
   // the caller may or may not pass cached norms: size for the larger of the two plans
   size_t parts = 0;
@@ -793,8 +932,17 @@ size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
     const size_t n = static_cast<size_t>(p.n_chunks) * Q * k;
     if (n > parts) parts = n;
   }
+  const size_t n_tiles = static_cast<size_t>((N + BLOCK_N - 1) / BLOCK_N);
   return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 +
-         align_up(static_cast<size_t>(Q) * 4, 256) + 256;
+         align_up(static_cast<size_t>(Q) * 4, 256) + align_up(n_tiles * 4, 256) + 256;
+}
+
+// In-kernel norm producers for uncached multi-tile batches (the pair kernel's NORMS_INSIDE
+// variant) instead of the streaming pre-pass.  IRR_NORMS_INSIDE=0 restores the pre-pass
+// (measurement knob for profiles/, not an API).
+bool norms_inside_enabled() {
+  const char* e = getenv("IRR_NORMS_INSIDE");
+  return !(e && e[0] == '0');
 }
 
 irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
@@ -818,14 +966,24 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   int32_t* pi = reinterpret_cast<int32_t*>(w);
   w += align_up(parts * 4, 256);
   uint32_t* row_floor = reinterpret_cast<uint32_t*>(w);
-  IRR_CUDA_TRY(cudaMemsetAsync(row_floor, 0, static_cast<size_t>(Q) * 4, st));
+  w += align_up(static_cast<size_t>(Q) * 4, 256);
+  uint32_t* tile_done = reinterpret_cast<uint32_t*>(w);
+  const bool inside = pair && !cached && norms_inside_enabled();
+  // one memset: the rows' shared floors and (if used) the per-tile norm counters
+  IRR_CUDA_TRY(cudaMemsetAsync(
+      row_floor, 0,
+      inside ? align_up(static_cast<size_t>(Q) * 4, 256) + static_cast<size_t>(p.n_tiles) * 4
+             : static_cast<size_t>(Q) * 4,
+      st));
 
   // single query tile and no cached norms: fuse the gallery norms into the tile stream;
   // otherwise the norms come from the caller's cache or from one streaming pre-pass
   // fuse the gallery norms into the tile stream when every gallery tile has exactly one consumer
   const bool fuse = !cached && !pair && p.m_tiles == 1;
   const float* gin = g_inv_norm;
-  if (!gin && !fuse) {
+  if (inside) {
+    gin = gin_ws;   // written by the kernel's own norm producers
+  } else if (!gin && !fuse) {
     irr_status s = row_inv_norms(g, N, D, dt, eps, gin_ws, st);
     if (s != IRR_OK) return s;
     gin = gin_ws;
@@ -836,10 +994,11 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
     return IRR_ERR_UNSUPPORTED_DEVICE;
   irr_status s;
   if (pair) {
-    if (k <= 4)
-      s = launch_pair<4>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, f16, st);
-    else
-      s = launch_pair<16>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, f16, st);
+#define IRR_LAUNCH_PAIR(KM, NI) \
+  s = launch_pair<KM, NI>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, f16, g, eps, tile_done, st)
+    if (inside) { if (k <= 4) IRR_LAUNCH_PAIR(4, true); else IRR_LAUNCH_PAIR(16, true); }
+    else        { if (k <= 4) IRR_LAUNCH_PAIR(4, false); else IRR_LAUNCH_PAIR(16, false); }
+#undef IRR_LAUNCH_PAIR
   } else {
     // (KMAX, fused norms, query tiles per unit) -> instantiation
 #define IRR_LAUNCH_SC(KM, FN, MTV)                                                              \
