@@ -968,7 +968,10 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   uint32_t* row_floor = reinterpret_cast<uint32_t*>(w);
   w += align_up(static_cast<size_t>(Q) * 4, 256);
   uint32_t* tile_done = reinterpret_cast<uint32_t*>(w);
-  const bool inside = pair && !cached && norms_inside_enabled();
+  // with one or two query-tile pairs the tile stream consumes the gallery faster than four producer
+  // warps per CTA can normalise it (measured: 512 queries 1.69 vs 1.66 ms with the pre-pass, 768
+  // queries 2.14 vs 2.54 ms): from three pairs on the producers win
+  const bool inside = pair && !cached && p.m_tiles >= 3 && norms_inside_enabled();
   // one memset: the rows' shared floors and (if used) the per-tile norm counters
   IRR_CUDA_TRY(cudaMemsetAsync(
       row_floor, 0,

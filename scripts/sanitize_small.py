@@ -39,5 +39,22 @@ fm = torch.randn(3, 130, 7, 7, device=dev, requires_grad=True)
 irr.get_fm(fm).sum().backward()
 la, lb = torch.randn(20, 125, device=dev, requires_grad=True), torch.randn(20, 125, device=dev, requires_grad=True)
 irr.cross_entropy_pair(la, lb, torch.randint(0, 125, (20,), device=dev)).loss.backward()
+# fp16 rows on the tensor path, streamed host gallery, peer-exchange protocol (virtual ranks)
+gh = torch.randn(3000, 256, device=dev).half()
+irr.cosine_topk(torch.randn(600, 256, device=dev).half(), gh, 3, fp16_tensor_path=True)
+irr.cosine_topk(torch.randn(5, 256, device=dev).half(), gh, 3, fp16_tensor_path=True)
+irr.StreamedGallery(torch.randn(2000, 64).bfloat16().pin_memory(), 700, dev).search(
+    torch.randn(9, 64, device=dev).bfloat16(), 3)
+from imageretrievalresearch_b200 import _lib
+G, Q, k = 3, 50, 3
+nb = _ops.topk_exchange_bytes(G, Q, k)
+bufs = [torch.zeros(nb, dtype=torch.uint8, device=dev) for _ in range(G)]
+ptrs = [b.data_ptr() for b in bufs]
+xv = torch.randn(G, Q, k, device=dev).sort(dim=2, descending=True).values
+xi = torch.randint(0, 1000, (G, Q, k), device=dev)
+for r in range(1, G):
+    _ops.topk_exchange_merge(xv[r], xi[r], ptrs, r, Q, k, nb, _lib.IRR_XCHG_PUSH, torch.device(dev, 0))
+_ops.topk_exchange_merge(xv[0], xi[0], ptrs, 0, Q, k, nb, _lib.IRR_XCHG_FUSED, torch.device(dev, 0))
+_ops.topk_exchange_merge(None, None, ptrs, 1, Q, k, nb, _lib.IRR_XCHG_MERGE, torch.device(dev, 0))
 torch.cuda.synchronize()
 print("sanitize_small: all kernels ran")
