@@ -10,7 +10,7 @@ from ._lib import IRR_MAX_K, IrrError, LIB_PATH, load as load_library
 from .losses import (ContrastiveLoss, CosineEmbeddingLoss, TripletFwdBwd, TripletLosses,
                      triplet_losses, triplet_losses_fwd_bwd)
 from .producer_consumer import CEPair, cross_entropy_pair, get_fm
-from .retrieval import (CapturedSearch, CosineSimilarity, DedupTopK, Gallery, TopK, class_dedup_topk, cosine_topk,
+from .retrieval import (CapturedSearch, CosineSimilarity, DedupTopK, Gallery, SearchPipeline, TopK, class_dedup_topk, cosine_topk,
                         top1_top3, top1_top3_dedup, topk_hits)
 from .store import (GalleryStore, GalleryWriter, StreamedGallery, block_ranges, gather_embeddings,
                     write_gallery)
@@ -23,5 +23,5 @@ __all__ = [
     "CosineSimilarity", "Gallery", "TopK", "DedupTopK", "cosine_topk", "top1_top3", "topk_hits",
     "class_dedup_topk", "top1_top3_dedup", "get_fm", "cross_entropy_pair", "CEPair",
     "GalleryStore", "GalleryWriter", "StreamedGallery", "write_gallery", "gather_embeddings",
-    "block_ranges", "ShardedGallery", "PeerExchange", "CapturedSearch", "exchange_candidates", "shard_bounds",
+    "block_ranges", "ShardedGallery", "PeerExchange", "CapturedSearch", "SearchPipeline", "exchange_candidates", "shard_bounds",
 ]

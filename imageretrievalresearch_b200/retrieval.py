@@ -226,3 +226,76 @@ class CapturedSearch:
             self.queries.copy_(queries)
         self.graph.replay()
         return self.result
+
+
+class SearchPipeline:
+    """Serving loop over host-resident query batches with copy / search / read-back overlap.
+
+    The reference's inference loop moves one batch at a time to the GPU, runs its per-query loop
+    and pulls every index back with ``.item()`` (inference/inference.py:225-245).  Here batch i+1 is
+    copied host->device on a copy stream while batch i is searched, and batch i's ``[Q,k]`` lists
+    travel back to pinned host memory on a third stream while batch i+1 is searched; the host only
+    waits for the batch it is about to hand out.  ``search_fn(queries, k)`` is any of the searches
+    of this package (``Gallery.search``, ``ShardedGallery.search``, a ``CapturedSearch``...).
+    """
+
+    def __init__(self, search_fn, num_queries: int, dim: int, k: int, dtype: torch.dtype,
+                 device: torch.device, depth: int = 2) -> None:
+        if depth < 2:
+            raise ValueError("depth >= 2: one batch in flight while the next is being copied")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("SearchPipeline feeds a CUDA device (there is no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.search_fn, self.k, self.depth, self.device = search_fn, k, depth, device
+        self.shape, self.dtype = (num_queries, dim), dtype
+        self._q = [torch.empty(self.shape, dtype=dtype, device=device) for _ in range(depth)]
+        # one more result slot than batches in flight: what was handed out stays untouched until
+        # the caller asks for the next batch
+        self._v = [torch.empty((num_queries, k), dtype=torch.float32).pin_memory() for _ in range(depth + 1)]
+        self._i = [torch.empty((num_queries, k), dtype=torch.int64).pin_memory() for _ in range(depth + 1)]
+        self._h2d, self._d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        self._landed = [torch.cuda.Event() for _ in range(depth)]    # queries of slot s on the device
+        self._searched = [torch.cuda.Event() for _ in range(depth)]  # search of slot s enqueued & done
+        self._back = [torch.cuda.Event() for _ in range(depth + 1)]  # results of slot r on the host
+        self.h2d_bytes_per_batch = num_queries * dim * torch.empty((), dtype=dtype).element_size()
+        self.d2h_bytes_per_batch = num_queries * k * 12
+
+    def _enqueue(self, s: int, r: int, q_host: torch.Tensor, used: bool) -> None:
+        if tuple(q_host.shape) != self.shape or q_host.dtype != self.dtype or q_host.is_cuda:
+            raise ValueError(f"expected a host batch {self.shape} of {self.dtype}")
+        cur = torch.cuda.current_stream(self.device)
+        if used:
+            self._h2d.wait_event(self._searched[s])      # slot's previous search has read its queries
+        with torch.cuda.stream(self._h2d):
+            self._q[s].copy_(q_host, non_blocking=True)
+            self._landed[s].record(self._h2d)
+        cur.wait_event(self._landed[s])
+        res = self.search_fn(self._q[s], self.k)
+        self._searched[s].record(cur)
+        self._d2h.wait_event(self._searched[s])
+        with torch.cuda.stream(self._d2h):
+            res.values.record_stream(self._d2h)
+            res.indices.record_stream(self._d2h)
+            self._v[r].copy_(res.values, non_blocking=True)
+            self._i[r].copy_(res.indices, non_blocking=True)
+            self._back[r].record(self._d2h)
+
+    def run(self, host_batches):
+        """Yield (values, indices) — pinned host tensors, valid until the next batch is requested —
+        for every batch of ``host_batches`` (pinned host ``[Q, D]`` tensors), in order."""
+        pending = []          # result slots in flight, oldest first
+        n = 0
+        for q_host in host_batches:
+            if len(pending) == self.depth:               # hand out the oldest batch first
+                r = pending.pop(0)
+                self._back[r].synchronize()
+                yield self._v[r], self._i[r]
+            r = n % (self.depth + 1)
+            self._enqueue(n % self.depth, r, q_host, used=n >= self.depth)
+            pending.append(r)
+            n += 1
+        for r in pending:
+            self._back[r].synchronize()
+            yield self._v[r], self._i[r]

@@ -582,6 +582,55 @@ def test_captured_search_replays_bit_identically(Q, k, dtype):
     assert torch.equal(again.indices, want.indices)
 
 
+def test_search_pipeline_overlapped_batches():
+    """SearchPipeline: host batches in, host results out, copies overlapped with the searches —
+    every batch's result equals the plain search of that batch."""
+    N, D, Q, k = 30_000, 256, 100, 3
+    _, gal = synthetic.iid_gallery(N, D, 1, seed=21, dtype=torch.bfloat16)
+    g = irr.Gallery(gal.cuda())
+    batches = [synthetic.iid_gallery(4, D, Q, seed=30 + i, dtype=torch.bfloat16)[0].pin_memory()
+               for i in range(7)]
+    for depth in (2, 3):
+        pipe = irr.SearchPipeline(g.search, Q, D, k, torch.bfloat16, "cuda", depth=depth)
+        got = [(v.clone(), i.clone()) for v, i in pipe.run(iter(batches))]
+        assert len(got) == len(batches)
+        for (v, i), qb in zip(got, batches):
+            want = g.search(qb.cuda(), k)
+            assert torch.equal(i, want.indices.cpu()) and torch.equal(v, want.values.cpu())
+    with pytest.raises(ValueError):
+        list(irr.SearchPipeline(g.search, Q, D, k, torch.bfloat16, "cuda").run([batches[0][:5]]))
+
+
+def test_sharded_c_entry_single_rank():
+    """irr_cosine_topk_sharded with G=1 (the exchange degenerates to a self-push): equals
+    irr_cosine_topk, and the buffer's epoch advances once per call."""
+    import ctypes as C
+    from imageretrievalresearch_b200 import _lib
+    lib = _lib.load()
+    Q, N, D, k = 70, 5000, 256, 3
+    q, gal = synthetic.iid_gallery(N, D, Q, seed=9, dtype=torch.bfloat16)
+    q, gal = q.cuda(), gal.cuda()
+    want = irr.cosine_topk(q, gal, k, idx_offset=1000)
+    nbytes = lib.irr_topk_exchange_bytes(1, Q, k)
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    peers = (C.c_void_p * 1)(buf.data_ptr())
+    need = lib.irr_cosine_topk_sharded_workspace_bytes(Q, N, D, k, _lib.IRR_BF16)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    ov = torch.empty(Q, k, dtype=torch.float32, device="cuda")
+    oi = torch.empty(Q, k, dtype=torch.int64, device="cuda")
+    for _ in range(3):
+        st = lib.irr_cosine_topk_sharded(q.data_ptr(), gal.data_ptr(), None, Q, N, D, k, _lib.IRR_BF16,
+                                         1e-6, 1000, peers, 1, 0, nbytes, ov.data_ptr(), oi.data_ptr(),
+                                         ws.data_ptr(), need, torch.cuda.current_stream().cuda_stream)
+        assert st == 0, lib.irr_status_string(st)
+        assert torch.equal(oi, want.indices) and torch.equal(ov, want.values)
+    assert int(buf[256:260].view(torch.int32).item()) == 3
+    st = lib.irr_cosine_topk_sharded(q.data_ptr(), gal.data_ptr(), None, Q, N, D, k, _lib.IRR_BF16, 1e-6,
+                                     0, peers, 1, 0, nbytes, ov.data_ptr(), oi.data_ptr(), ws.data_ptr(),
+                                     need - 1, torch.cuda.current_stream().cuda_stream)
+    assert st == -4
+
+
 def test_dedup_edge_cases():
     # fewer distinct classes than requested, padding entries, n_distinct = 1
     idx = torch.tensor([[0, 1, 2, 3], [4, 4, 5, -1], [6, -1, -1, -1]])
