@@ -159,6 +159,31 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, i
   }
 }
 
+// Fused-norm warps: square-sum this thread's two gallery rows (64 elements each) of one stage.
+// Logical chunk order (position j ^ (row & 7) under the 128-byte swizzle), see the kernel.
+template <bool F16>
+__device__ __forceinline__ void norm_stage_sums(const uint4* r0, const uint4* r1, int nt, float& s0a,
+                                                float& s0b, float& s1a, float& s1b) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const uint4 u0 = r0[j ^ (nt & 7)], u1 = r0[(j + 1) ^ (nt & 7)];
+    const uint4 w0 = r1[j ^ (nt & 7)], w1 = r1[(j + 1) ^ (nt & 7)];
+    const uint32_t x0[4] = {u0.x, u0.y, u0.z, u0.w}, x1[4] = {u1.x, u1.y, u1.z, u1.w};
+    const uint32_t y0[4] = {w0.x, w0.y, w0.z, w0.w}, y1[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = unpack16x2(x0[e], F16);
+      s0a = fmaf(f.x, f.x, s0a); s0a = fmaf(f.y, f.y, s0a);
+      f = unpack16x2(x1[e], F16);
+      s0b = fmaf(f.x, f.x, s0b); s0b = fmaf(f.y, f.y, s0b);
+      f = unpack16x2(y0[e], F16);
+      s1a = fmaf(f.x, f.x, s1a); s1a = fmaf(f.y, f.y, s1a);
+      f = unpack16x2(y1[e], F16);
+      s1b = fmaf(f.x, f.x, s1b); s1b = fmaf(f.y, f.y, s1b);
+    }
+  }
+}
+
 // row_floor[Q]: orderable(k-th best score) each row has reached in ANY gallery chunk so far
 // (0 = none yet; zeroed before every launch).  Chunks of the same rows run on other CTAs at the same
 // time or earlier; reading the floor once per tile lets every chunk start with a warm threshold
@@ -356,24 +381,10 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint8_t* b = smem_gen + stage * STAGE_BYTES + G::A_BYTES;
           const uint4* r0 = reinterpret_cast<const uint4*>(b + nt * 128);
           const uint4* r1 = reinterpret_cast<const uint4*>(b + (nt + NORM_THREADS) * 128);
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const uint4 u0 = r0[j ^ (nt & 7)], u1 = r0[(j + 1) ^ (nt & 7)];
-            const uint4 w0 = r1[j ^ (nt & 7)], w1 = r1[(j + 1) ^ (nt & 7)];
-            const uint32_t x0[4] = {u0.x, u0.y, u0.z, u0.w}, x1[4] = {u1.x, u1.y, u1.z, u1.w};
-            const uint32_t y0[4] = {w0.x, w0.y, w0.z, w0.w}, y1[4] = {w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f = unpack16x2(x0[e], is_f16 != 0);
-              s0a = fmaf(f.x, f.x, s0a); s0a = fmaf(f.y, f.y, s0a);
-              f = unpack16x2(x1[e], is_f16 != 0);
-              s0b = fmaf(f.x, f.x, s0b); s0b = fmaf(f.y, f.y, s0b);
-              f = unpack16x2(y0[e], is_f16 != 0);
-              s1a = fmaf(f.x, f.x, s1a); s1a = fmaf(f.y, f.y, s1a);
-              f = unpack16x2(y1[e], is_f16 != 0);
-              s1b = fmaf(f.x, f.x, s1b); s1b = fmaf(f.y, f.y, s1b);
-            }
-          }
+          // one branch per stage, not one select per element: these four warps have to keep pace
+          // with the HBM stream
+          if (is_f16) norm_stage_sums<true>(r0, r1, nt, s0a, s0b, s1a, s1b);
+          else        norm_stage_sums<false>(r0, r1, nt, s0a, s0b, s1a, s1b);
           __syncwarp();
           if (lane == 0) mbar_arrive(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -513,6 +524,71 @@ static __device__ __noinline__ void wait_tile_norms_slow(const uint32_t* cnt, ui
   }
 }
 
+// One octet of gallery rows -> 1/max(|g|,eps), by one warp of the in-kernel norm producers.
+// PACED producers read with the default L2 policy (the TMA loads of the same tile follow within a
+// few tiles and should hit those lines); unpaced ones run far ahead and read evict-first.
+template <bool F16, bool PACED>
+__device__ __forceinline__ void norm_octet(const uint4* __restrict__ g_rows, int vec_per_row, int row0,
+                                           int rows, float eps, float* __restrict__ norm_out, int lane) {
+  // four rows at a time, four 16-byte vectors per row and lane in flight (16 independent loads
+  // per lane = 8 KB per warp): the producers have to keep pace with the tile stream, which for a
+  // few hundred queries consumes the gallery at several TB/s
+  for (int r = 0; r < rows; r += 4) {
+    const uint4* base = g_rows + static_cast<size_t>(row0 + r) * vec_per_row;
+    const int nr = min(4, rows - r);
+    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+    int v = lane;
+    for (; v + 96 < vec_per_row; v += 128) {
+      uint4 u[4][4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          u[rr][c] = rr >= nr ? make_uint4(0u, 0u, 0u, 0u)
+                     : PACED ? ldg_stream(base + rr * vec_per_row + v + 32 * c)
+                             : ldg_stream_evict_first(base + rr * vec_per_row + v + 32 * c);
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t w[4] = {u[rr][c].x, u[rr][c].y, u[rr][c].z, u[rr][c].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack16x2(w[e], F16);
+            ss[rr] = fmaf(f.x, f.x, ss[rr]);
+            ss[rr] = fmaf(f.y, f.y, ss[rr]);
+          }
+        }
+      }
+    }
+    for (; v < vec_per_row; v += 32) {
+      uint4 u[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+        u[rr] = rr >= nr ? make_uint4(0u, 0u, 0u, 0u)
+                : PACED ? ldg_stream(base + rr * vec_per_row + v)
+                        : ldg_stream_evict_first(base + rr * vec_per_row + v);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const uint32_t w[4] = {u[rr].x, u[rr].y, u[rr].z, u[rr].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack16x2(w[e], F16);
+          ss[rr] = fmaf(f.x, f.x, ss[rr]);
+          ss[rr] = fmaf(f.y, f.y, ss[rr]);
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) ss[rr] = warp_sum(ss[rr]);
+    if (lane < nr) {
+      const float mine = lane == 0 ? ss[0] : lane == 1 ? ss[1] : lane == 2 ? ss[2] : ss[3];
+      norm_out[row0 + r + lane] = 1.0f / fmaxf(sqrtf(mine), eps);
+    }
+  }
+}
+
 // NORMS_INSIDE (no cached norms): instead of a streaming pre-pass kernel, four extra warps per CTA
 // compute 1/max(|g|,eps) for the WHOLE gallery cooperatively across the grid, straight from global
 // memory, in the order the tile stream will need the tiles (the chunks that start together are
@@ -532,7 +608,8 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                              float* __restrict__ part_val, int32_t* __restrict__ part_idx,
                              uint32_t* __restrict__ row_floor, int is_f16,
                              const uint4* __restrict__ g_rows, int vec_per_row, float eps,
-                             float* __restrict__ norm_out, uint32_t* __restrict__ tile_rows_done) {
+                             float* __restrict__ norm_out, uint32_t* __restrict__ tile_rows_done,
+                             int norm_ahead) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -546,6 +623,11 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   float* gn_smem = reinterpret_cast<float*>(smem_gen + P_SMEM_TILES);
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + P_SMEM_TILES + SMEM_GN + P_SMEM_BARS);
+
+  // NORMS_INSIDE: this CTA's position on the tile stream's timeline (wave * tiles_per_chunk + tile
+  // in chunk), published by the epilogue, read by the CTA's norm producers to pace themselves
+  volatile int* stream_pos = reinterpret_cast<volatile int*>(smem_gen + P_SMEM_TILES + SMEM_GN + P_SMEM_BARS + 8);
+  if (NORMS_INSIDE && threadIdx.x == 0) *stream_pos = 0;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -642,77 +724,42 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ===================== gallery-norm producers (whole grid, need order) =====================
     const int nw = static_cast<int>(blockIdx.x) * 4 + (warp - P_NORM_WARP0);
     const int NW = static_cast<int>(gridDim.x) * 4;
-    const int group = (num_clusters + m_pairs - 1) / m_pairs;      // chunks that start together
-    const long long slots_per_group = 1ll * tiles_per_chunk * group * OCTETS_PER_TILE;
-    const long long total_slots = slots_per_group * ((n_chunks + group - 1) / group);
+    // Slots (one octet of rows each) in the order the tile stream needs them: wave by wave (a wave
+    // = one unit per cluster), inside a wave tile by tile, inside a tile position the chunks whose
+    // first unit runs in that wave.  key = wave * tiles_per_chunk + tile-in-chunk is the slot's
+    // place on the same timeline as stream_pos; a producer does not run more than norm_ahead tiles
+    // ahead of its own CTA's epilogue, so that its DRAM reads are the ones the TMA loads of the
+    // same tile then find in L2 (one DRAM read of the gallery serves both) — all CTAs move along
+    // the timeline at the same pace, and the slowest CTA's needs are never held back (its key is
+    // <= everybody's position), so pacing cannot deadlock.
+    const long long slots_per_chunk = 1ll * tiles_per_chunk * OCTETS_PER_TILE;
+    const long long total_slots = slots_per_chunk * n_chunks;
     const bool f16 = is_f16 != 0;
+    const bool paced = norm_ahead >= 0;
     for (long long o = nw; o < total_slots; o += NW) {
-      const int grp = static_cast<int>(o / slots_per_group);
-      const int rem = static_cast<int>(o - grp * slots_per_group);
-      const int j = rem / (group * OCTETS_PER_TILE);
-      const int r2 = rem - j * (group * OCTETS_PER_TILE);
-      const int chunk = grp * group + r2 / OCTETS_PER_TILE;
+      const long long cq = o / slots_per_chunk;
+      const int w = static_cast<int>(cq * m_pairs / num_clusters);
+      const int c_lo = static_cast<int>((1ll * w * num_clusters + m_pairs - 1) / m_pairs);
+      const int c_hi = min(static_cast<int>((1ll * (w + 1) * num_clusters + m_pairs - 1) / m_pairs), n_chunks);
+      const int nch = c_hi - c_lo;
+      const int rem = static_cast<int>(o - c_lo * slots_per_chunk);
+      const int j = rem / (nch * OCTETS_PER_TILE);
+      const int r2 = rem - j * (nch * OCTETS_PER_TILE);
+      const int chunk = c_lo + r2 / OCTETS_PER_TILE;
       const int oct = r2 % OCTETS_PER_TILE;
-      if (chunk >= n_chunks) continue;
       const int tile = chunk * tiles_per_chunk + j;
-      if (tile >= n_tiles || tile >= (chunk + 1) * tiles_per_chunk) continue;
+      if (tile >= n_tiles) continue;
+      if (paced) {
+        const int key = w * tiles_per_chunk + j;
+        while (key > *stream_pos + norm_ahead) __nanosleep(256);
+      }
       const int row0 = tile * BLOCK_N + oct * OCTET;
       if (row0 >= N) continue;
       const int rows = min(OCTET, N - row0);
-      // four rows at a time, four 16-byte vectors per row and lane in flight (16 independent loads
-      // per lane = 8 KB per warp): the producers have to keep pace with the tile stream, which for a
-      // few hundred queries consumes the gallery at several TB/s
-      for (int r = 0; r < rows; r += 4) {
-        const uint4* base = g_rows + static_cast<size_t>(row0 + r) * vec_per_row;
-        const int nr = min(4, rows - r);
-        float ss[4] = {0.f, 0.f, 0.f, 0.f};
-        int v = lane;
-        for (; v + 96 < vec_per_row; v += 128) {
-          uint4 u[4][4];
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              u[rr][c] = rr < nr ? ldg_stream_evict_first(base + rr * vec_per_row + v + 32 * c)
-                                 : make_uint4(0u, 0u, 0u, 0u);
-          }
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t w[4] = {u[rr][c].x, u[rr][c].y, u[rr][c].z, u[rr][c].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack16x2(w[e], f16);
-                ss[rr] = fmaf(f.x, f.x, ss[rr]);
-                ss[rr] = fmaf(f.y, f.y, ss[rr]);
-              }
-            }
-          }
-        }
-        for (; v < vec_per_row; v += 32) {
-          uint4 u[4];
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr)
-            u[rr] = rr < nr ? ldg_stream_evict_first(base + rr * vec_per_row + v) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const uint32_t w[4] = {u[rr].x, u[rr].y, u[rr].z, u[rr].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack16x2(w[e], f16);
-              ss[rr] = fmaf(f.x, f.x, ss[rr]);
-              ss[rr] = fmaf(f.y, f.y, ss[rr]);
-            }
-          }
-        }
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) ss[rr] = warp_sum(ss[rr]);
-        if (lane < nr) {
-          const float mine = lane == 0 ? ss[0] : lane == 1 ? ss[1] : lane == 2 ? ss[2] : ss[3];
-          norm_out[row0 + r + lane] = 1.0f / fmaxf(sqrtf(mine), eps);
-        }
-      }
+      if (f16) { if (paced) norm_octet<true, true>(g_rows, vec_per_row, row0, rows, eps, norm_out, lane);
+                 else       norm_octet<true, false>(g_rows, vec_per_row, row0, rows, eps, norm_out, lane); }
+      else     { if (paced) norm_octet<false, true>(g_rows, vec_per_row, row0, rows, eps, norm_out, lane);
+                 else       norm_octet<false, false>(g_rows, vec_per_row, row0, rows, eps, norm_out, lane); }
       __syncwarp();
       if (lane == 0) {
         __threadfence();                                  // the octet's norms before its count
@@ -741,6 +788,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         {
           const int c0 = n0 + et, c1 = n0 + et + EPI_THREADS;
           if (NORMS_INSIDE) {
+            if (et == 0) *stream_pos = (u / num_clusters) * tiles_per_chunk + (t - t0);
             // producers publish rows in octets; the tile is usable once all of its rows are counted
             if (lane == 0) {
               const uint32_t need = static_cast<uint32_t>(min(BLOCK_N, N - n0));
@@ -777,6 +825,8 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     }
+    // done with the tile stream: this CTA's producers finish whatever is left unpaced
+    if (NORMS_INSIDE && et == 0) *stream_pos = 0x3fffffff;
   }
 
   // neither CTA may leave (or free TMEM) while its partner can still read its shared memory,
@@ -832,6 +882,16 @@ bool use_pair(int64_t Q, bool cached_norms) {
   return Q > 3 * BLOCK_M;
 }
 
+// How many tiles the in-kernel norm producers may run ahead of their CTA's epilogue (see the
+// kernel).  IRR_NORM_AHEAD overrides (negative = unpaced); measurement knob, not an API.
+int norm_ahead_tiles() {
+  static int cached = []() {
+    const char* e = getenv("IRR_NORM_AHEAD");
+    return e ? atoi(e) : 2;
+  }();
+  return cached;
+}
+
 // norms_inside: gin is the (not yet filled) fp32[N] buffer the in-kernel producers write and the
 // epilogues read; tile_done is the zeroed per-tile row counter array
 template <int KMAX, bool NORMS_INSIDE>
@@ -846,7 +906,7 @@ irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float
   kern<<<p.grid, NORMS_INSIDE ? P_THREADS_NORM : P_THREADS, P_SMEM_ALLOC, st>>>(
       tq, tg, gin, static_cast<int>(Q), static_cast<int>(N), num_kb, k, p.m_tiles, p.n_tiles,
       p.tiles_per_chunk, p.n_chunks, pv, pi, row_floor, f16 ? 1 : 0, static_cast<const uint4*>(g),
-      D * 2 / 16, eps, const_cast<float*>(gin), tile_done);
+      D * 2 / 16, eps, const_cast<float*>(gin), tile_done, norm_ahead_tiles());
   profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -940,6 +1000,13 @@ size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
 // In-kernel norm producers for uncached multi-tile batches (the pair kernel's NORMS_INSIDE
 // variant) instead of the streaming pre-pass.  IRR_NORMS_INSIDE=0 restores the pre-pass
 // (measurement knob for profiles/, not an API).
+int norms_inside_min_pairs() {
+  static int cached = []() {
+    const char* e = getenv("IRR_NORMS_MIN_PAIRS");
+    return e ? atoi(e) : 3;
+  }();
+  return cached;
+}
 bool norms_inside_enabled() {
   const char* e = getenv("IRR_NORMS_INSIDE");
   return !(e && e[0] == '0');
@@ -971,7 +1038,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   // with one or two query-tile pairs the tile stream consumes the gallery faster than four producer
   // warps per CTA can normalise it (measured: 512 queries 1.69 vs 1.66 ms with the pre-pass, 768
   // queries 2.14 vs 2.54 ms): from three pairs on the producers win
-  const bool inside = pair && !cached && p.m_tiles >= 3 && norms_inside_enabled();
+  const bool inside = pair && !cached && p.m_tiles >= norms_inside_min_pairs() && norms_inside_enabled();
   // one memset: the rows' shared floors and (if used) the per-tile norm counters
   IRR_CUDA_TRY(cudaMemsetAsync(
       row_floor, 0,
