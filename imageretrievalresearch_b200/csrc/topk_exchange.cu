@@ -193,7 +193,7 @@ exchange_wait_kernel(const uint8_t* __restrict__ mine, int G, unsigned long long
 
 unsigned long long exchange_timeout_ns() {
   static unsigned long long cached = []() -> unsigned long long {
-    long ms = 30000;
+    long ms = 600000;   // a late peer is waited for as long as a collective library would
     if (const char* e = getenv("IRR_EXCHANGE_TIMEOUT_MS")) {
       const long v = atol(e);
       if (v > 0) ms = v;

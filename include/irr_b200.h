@@ -147,7 +147,7 @@ IRR_API irr_status irr_topk_merge_strided(const float* cand_val, int64_t val_ran
  * this rank's own buffer.  One kernel stores this rank's [Q,k] list into slot `rank` of every
  * buffer over NVLink, publishes the call's epoch to each peer (st.release.sys), waits until all G
  * lists of the epoch have landed locally (ld.acquire.sys, watchdog IRR_EXCHANGE_TIMEOUT_MS,
- * default 30 s -> trap) and merges them like irr_topk_merge.  Every rank of the group must make
+ * default 600 s -> trap) and merges them like irr_topk_merge.  Every rank of the group must make
  * the same sequence of calls (same G, Q, k) on ONE stream per buffer; the epoch lives in the
  * buffer, so the launch is CUDA-graph capturable.  G <= IRR_MAX_PEERS.
  * mode: IRR_XCHG_FUSED the call described above; IRR_XCHG_PUSH store + publish only;

@@ -14,6 +14,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("IRR_EXCHANGE_TIMEOUT_MS", "20000")   # a check script: trap early, do not hang
 
 import torch
 import torch.distributed as dist
