@@ -182,6 +182,84 @@ def pool():
               flush=True)
 
 
+def train_step():
+    """The path's share of ONE training / validation step at the reference's own batch size
+    (train/train_efficient_cos_con_ce_loss.py:230-287,374-405; B=64 pooled 1536-d embeddings, fp32):
+    the reference's calls on the same GPU (four loss modules + backward, then the per-row
+    cos/topk loop with its host syncs, plus the validation step's paired-score loops) against
+    triplet_losses + backward + top1_top3 (+ the pair scores the fused loss already returns)."""
+    import torch.nn as nn
+    B, D = 64, 1536
+    torch.manual_seed(0)
+    mk = lambda: torch.randn(B, D, device="cuda", requires_grad=True)
+    fm_ims, fm_poss, fm_negs = mk(), mk(), mk()
+    clss = (torch.arange(B, device="cuda") % 8)
+    cos = nn.CosineSimilarity(dim=1, eps=1e-6)
+    cel = nn.CosineEmbeddingLoss(margin=0.3)
+    one, mone = torch.ones(1, device="cuda"), -torch.ones(1, device="cuda")
+
+    def con(a, b, y, m=0.3):      # utils/contrastive_loss.py:56-61
+        d = (b - a).pow(2).sum(1)
+        return (0.5 * (y * d + (1 - y) * torch.relu(m - (d + 1e-9).sqrt()).pow(2))).mean()
+
+    def ref_train(i):
+        loss = cel(fm_ims, fm_poss, one) + cel(fm_ims, fm_negs, mone) + con(fm_ims, fm_poss, 1.0) + con(fm_ims, fm_negs, 0.0)
+        loss.backward()
+        top3 = top1 = 0
+        for idx in range(B):
+            sim = cos(fm_ims[idx].unsqueeze(0), fm_poss)
+            vals, inds = torch.topk(sim, k=3)
+            if clss[idx] == clss[inds[0]] or clss[idx] == clss[inds[1]] or clss[idx] == clss[inds[2]]:
+                top3 += 1
+            if clss[idx] in clss[inds[0]]:
+                top1 += 1
+        fm_ims.grad = fm_poss.grad = fm_negs.grad = None
+        return top1, top3
+
+    def ref_val(i):
+        with torch.no_grad():
+            cel(fm_ims, fm_poss, one); cel(fm_ims, fm_negs, mone); con(fm_ims, fm_poss, 1.0); con(fm_ims, fm_negs, 0.0)
+            sims, unsims, top3, top1 = [], [], 0, 0
+            for idx in range(B):
+                sims.append(cos(fm_ims[idx].unsqueeze(0), fm_poss[idx].unsqueeze(0)))
+                unsims.append(cos(fm_ims[idx].unsqueeze(0), fm_negs[idx].unsqueeze(0)))
+                sim = cos(fm_ims[idx].unsqueeze(0), fm_poss)
+                vals, inds = torch.topk(sim, k=3)
+                if clss[idx] == clss[inds[0]] or clss[idx] == clss[inds[1]] or clss[idx] == clss[inds[2]]:
+                    top3 += 1
+                if clss[idx] in clss[inds[0]]:
+                    top1 += 1
+            return torch.mean(torch.FloatTensor(sims)).item(), torch.mean(torch.FloatTensor(unsims)).item()
+
+    def ours_train(i):
+        tl = irr.triplet_losses(fm_ims, fm_poss, fm_negs, 0.3)
+        (tl.loss_cos + tl.loss_con).backward()
+        t1, t3, _ = irr.top1_top3(fm_ims, fm_poss, clss, clss, k=3)
+        fm_ims.grad = fm_poss.grad = fm_negs.grad = None
+        return t1, t3
+
+    def ours_val(i):
+        with torch.no_grad():
+            tl = irr.triplet_losses(fm_ims, fm_poss, fm_negs, 0.3, pair_scores=True)
+            t1, t3, _ = irr.top1_top3(fm_ims, fm_poss, clss, clss, k=3)
+            return tl.pair_cos_pos.mean().item(), tl.pair_cos_neg.mean().item()
+
+    for name, fn, n in (("reference calls on the GPU, training step", ref_train, 10),
+                        ("this package, training step", ours_train, 200),
+                        ("reference calls on the GPU, validation step", ref_val, 10),
+                        ("this package, validation step", ours_val, 200)):
+        fn(0)
+        torch.cuda.synchronize()
+        import time
+        t0 = time.perf_counter()
+        for i in range(n):
+            fn(i)
+        torch.cuda.synchronize()
+        us = (time.perf_counter() - t0) / n * 1e6
+        print(json.dumps({"what": "hot-path share of one step, B=64 x 1536 fp32 (wall clock, host syncs included)",
+                          "who": name, "us": us}), flush=True)
+
+
 def streamed():
     """Host-resident gallery scanned block by block (StreamedGallery): bound by the host link."""
     N, D = 1_000_000, 1536
