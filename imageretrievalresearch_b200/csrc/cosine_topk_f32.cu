@@ -8,6 +8,8 @@
 // tile goes to shared memory once, and 64 threads (one per query row) fold it into their running
 // sorted top-k in increasing column order.  Work unit = (query tile, chunk of gallery tiles); the
 // per-unit partial lists are folded by topk_merge.cu.
+#include <stdlib.h>
+
 #include "irr_common.cuh"
 #include "irr_kernels.h"
 
@@ -187,10 +189,230 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Large-batch variant (more than 64 queries): score tile 128 x 128, 8 x 8 register micro-tile per
+// thread, packed FFMA2 (two fp32 lanes per instruction: acc[i][2j], acc[i][2j+1] against the splat
+// of a[i] — each lane is an IEEE fp32 FMA and every output element still accumulates over k in
+// ascending order, so the scores are bit-identical to the 64 x 128 kernel's).  Per k step a thread
+// issues 4 LDS.128 + 32 FFMA2 for 64 FMAs (the small kernel: 3 LDS.128 + 32 FFMA for 32), which
+// takes instruction issue off the critical path.  The score tile aliases the operand buffers (they
+// are dead once the last K-slab is consumed) and the running top-k lists live in shared memory
+// between tiles, so the accumulators are the only large register-resident state (2 CTAs per SM).
+// ---------------------------------------------------------------------------------------------
+constexpr int GM = 128, GN = 128;
+constexpr int GA_LD = GM + 4, GB_LD = GN + 4, GS_LD = GN + 1;
+constexpr int G_SMEM_AB = 2 * BK * (GA_LD + GB_LD) * 4;        // double-buffered K-slabs
+constexpr int G_SMEM_S = GM * GS_LD * 4;                       // score tile (aliases the slabs)
+constexpr int G_SMEM_TILE = G_SMEM_AB > G_SMEM_S ? G_SMEM_AB : G_SMEM_S;
+
+template <int KMAX>
+constexpr int big_smem_bytes() { return G_SMEM_TILE + GM * KMAX * 8; }
+
+Plan make_plan_big(int64_t Q, int64_t N) {
+  Plan p;
+  p.m_tiles = static_cast<int>((Q + GM - 1) / GM);
+  p.n_tiles = static_cast<int>((N + GN - 1) / GN);
+  if (p.m_tiles < 1) p.m_tiles = 1;
+  if (p.n_tiles < 1) p.n_tiles = 1;
+  const int slots = num_sms() * 2;
+  int best = 1;
+  double best_cost = 1e300;
+  const int max_tpc = p.n_tiles < 64 ? p.n_tiles : 64;
+  for (int tpc = 1; tpc <= max_tpc; ++tpc) {
+    const long long units = 1ll * ((p.n_tiles + tpc - 1) / tpc) * p.m_tiles;
+    const long long waves = (units + slots - 1) / slots;
+    const double cost = static_cast<double>(waves) * (tpc + 0.1);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = tpc; }
+  }
+  p.tiles_per_chunk = best;
+  p.n_chunks = (p.n_tiles + best - 1) / best;
+  return p;
+}
+
+template <int KMAX, bool WRITE_SCORES>
+__global__ void __launch_bounds__(THREADS, 2)
+cosine_topk_f32_big_kernel(const float* __restrict__ q, const float* __restrict__ g,
+                           const float* __restrict__ g_inv_norm, int Q, int N, int D, int k,
+                           int m_tiles, int n_tiles, int tiles_per_chunk,
+                           float* __restrict__ part_val, int32_t* __restrict__ part_idx,
+                           const float* __restrict__ q_inv_norm, float* __restrict__ scores_out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float* As = reinterpret_cast<float*>(smem);                               // [2][BK][GA_LD]
+  float* Bs = As + 2 * BK * GA_LD;                                          // [2][BK][GB_LD]
+  float* Ss = reinterpret_cast<float*>(smem);                               // [GM][GS_LD], aliases As/Bs
+  float* Lv = reinterpret_cast<float*>(smem + G_SMEM_TILE);                 // [KMAX][GM] running lists
+  int32_t* Li = reinterpret_cast<int32_t*>(Lv + GM * KMAX);
+
+  const int t = threadIdx.x;
+  const int ty = t >> 4, tx = t & 15;
+  const int chunk = blockIdx.x / m_tiles, mt = blockIdx.x - chunk * m_tiles;
+  const int m0 = mt * GM;
+  const int t0 = chunk * tiles_per_chunk, t1 = min(t0 + tiles_per_chunk, n_tiles);
+
+  // global -> smem staging: A and B tiles are 128 rows x 16 k = 512 float4 each, two per thread
+  const float* a_src[2];
+  bool a_ok[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int f = t + i * THREADS;
+    const int row = f >> 2;
+    a_ok[i] = m0 + row < Q;
+    a_src[i] = q + static_cast<size_t>(a_ok[i] ? m0 + row : 0) * D + (f & 3) * 4;
+  }
+  if (!WRITE_SCORES && t < GM) {
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      Lv[j * GM + t] = kNegInf;
+      Li[j * GM + t] = -1;
+    }
+  }
+
+  const int num_ks = (D + BK - 1) / BK;
+  for (int tile = t0; tile < t1; ++tile) {
+    const int n0 = tile * GN;
+    const float* b_src[2];
+    bool b_ok[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = t + i * THREADS;
+      const int row = f >> 2;
+      b_ok[i] = n0 + row < N;
+      b_src[i] = g + static_cast<size_t>(b_ok[i] ? n0 + row : 0) * D + (f & 3) * 4;
+    }
+    float2 acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+    float4 ra[2], rb[2];
+    auto gload = [&](int ks) {
+      const int kk = ks * BK;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int kq = ((t + i * THREADS) & 3) * 4;
+        ra[i] = (a_ok[i] && kk + kq < D) ? __ldg(reinterpret_cast<const float4*>(a_src[i] + kk)) : z;
+        rb[i] = (b_ok[i] && kk + kq < D) ? __ldg(reinterpret_cast<const float4*>(b_src[i] + kk)) : z;
+      }
+    };
+    auto sstore = [&](int buf) {
+      float* a = As + buf * BK * GA_LD;
+      float* b = Bs + buf * BK * GB_LD;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int f = t + i * THREADS;
+        const int row = f >> 2, kq = (f & 3) * 4;
+        a[(kq + 0) * GA_LD + row] = ra[i].x;
+        a[(kq + 1) * GA_LD + row] = ra[i].y;
+        a[(kq + 2) * GA_LD + row] = ra[i].z;
+        a[(kq + 3) * GA_LD + row] = ra[i].w;
+        b[(kq + 0) * GB_LD + row] = rb[i].x;
+        b[(kq + 1) * GB_LD + row] = rb[i].y;
+        b[(kq + 2) * GB_LD + row] = rb[i].z;
+        b[(kq + 3) * GB_LD + row] = rb[i].w;
+      }
+    };
+
+    gload(0);
+    __syncthreads();  // previous tile's readers of the score tile (which aliases As/Bs) are done
+    sstore(0);
+    __syncthreads();
+    for (int ks = 0; ks < num_ks; ++ks) {
+      const int buf = ks & 1;
+      if (ks + 1 < num_ks) gload(ks + 1);
+      const float* a = As + buf * BK * GA_LD + ty * 4;
+      const float* b = Bs + buf * BK * GB_LD + tx * 4;
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(a + kk * GA_LD);
+        const float4 a1 = *reinterpret_cast<const float4*>(a + kk * GA_LD + 64);
+        const float4 b0 = *reinterpret_cast<const float4*>(b + kk * GB_LD);
+        const float4 b1 = *reinterpret_cast<const float4*>(b + kk * GB_LD + 64);
+        const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
+                              make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 as2 = make_float2(ar[i], ar[i]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(as2, bp[j], acc[i][j]);
+        }
+      }
+      if (ks + 1 < num_ks) {
+        sstore(buf ^ 1);
+        __syncthreads();
+      }
+    }
+    // scale by the inverse gallery norms and publish the tile (aliases the operand buffers: every
+    // thread must be done reading the last K-slab first)
+    float gn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      gn[j] = c < N ? __ldg(g_inv_norm + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = j < 2 ? tx * 4 + 2 * j : 64 + tx * 4 + 2 * (j - 2);
+        Ss[r * GS_LD + c] = acc[i][j].x * gn[2 * j];
+        Ss[r * GS_LD + c + 1] = acc[i][j].y * gn[2 * j + 1];
+      }
+    }
+    __syncthreads();
+    if (WRITE_SCORES) {
+      for (int e = t; e < GM * GN; e += THREADS) {
+        const int r = e / GN, c = e - r * GN;
+        if (m0 + r < Q && n0 + c < N)
+          scores_out[static_cast<size_t>(m0 + r) * N + n0 + c] =
+              Ss[r * GS_LD + c] * __ldg(q_inv_norm + m0 + r);
+      }
+    } else if (t < GM) {
+      TopKList<KMAX, int32_t> top;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        top.v[j] = Lv[j * GM + t];
+        top.i[j] = Li[j * GM + t];
+      }
+      const int n_valid = min(GN, N - n0);
+      const float* s = Ss + t * GS_LD;
+      for (int c = 0; c < n_valid; ++c) top.push_ordered(s[c], n0 + c);
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        Lv[j * GM + t] = top.v[j];
+        Li[j * GM + t] = top.i[j];
+      }
+    }
+  }
+  if (!WRITE_SCORES && t < GM && m0 + t < Q) {
+    const size_t o = (static_cast<size_t>(chunk) * Q + m0 + t) * k;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j < k) {
+        part_val[o + j] = Lv[j * GM + t];
+        part_idx[o + j] = Li[j * GM + t];
+      }
+  }
+}
+
+// IRR_F32_SMALL_TILES=1 forces the 64 x 128 kernel (measurement / bit-equality knob, not an API)
+bool use_big(int64_t Q) {
+  static const bool forced_small = []() {
+    const char* e = getenv("IRR_F32_SMALL_TILES");
+    return e && e[0] == '1';
+  }();
+  return Q > BM && !forced_small;
+}
+
 }  // namespace
 
 size_t f32_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
-  const Plan p = make_plan(Q, N);
+  const Plan p = use_big(Q) ? make_plan_big(Q, N) : make_plan(Q, N);
   const size_t parts = static_cast<size_t>(p.n_chunks) * Q * k;
   return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 + 256;
 }
@@ -201,7 +423,8 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
                            cudaStream_t st) {
   if (N > 0x7fffff00ll || Q > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
   if (ws_bytes < f32_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
-  const Plan p = make_plan(Q, N);
+  const bool big = use_big(Q);
+  const Plan p = big ? make_plan_big(Q, N) : make_plan(Q, N);
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* gin_ws = reinterpret_cast<float*>(w);
   w += align_up(static_cast<size_t>(N) * 4, 256);
@@ -218,7 +441,20 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
   }
   const int grid = p.m_tiles * p.n_chunks;
   profile_mark_start(st);
-  if (k <= 4) {
+  if (big) {
+#define IRR_LAUNCH_BIG(KM)                                                                        \
+  do {                                                                                            \
+    auto kern = cosine_topk_f32_big_kernel<KM, false>;                                            \
+    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                      big_smem_bytes<KM>()));                                     \
+    kern<<<grid, THREADS, big_smem_bytes<KM>(), st>>>(                                            \
+        static_cast<const float*>(q), static_cast<const float*>(g), gin, static_cast<int>(Q),     \
+        static_cast<int>(N), D, k, p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi, nullptr,      \
+        nullptr);                                                                                 \
+  } while (0)
+    if (k <= 4) IRR_LAUNCH_BIG(4); else IRR_LAUNCH_BIG(16);
+#undef IRR_LAUNCH_BIG
+  } else if (k <= 4) {
     auto kern = cosine_topk_f32_kernel<4, false>;
     IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(static_cast<const float*>(q), static_cast<const float*>(g),
@@ -242,6 +478,18 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
 irr_status f32_cosine_scores(const void* q, const void* g, const float* g_inv_norm,
                              const float* q_inv_norm, int64_t Q, int64_t N, int32_t D,
                              float* out_scores, cudaStream_t st) {
+  if (use_big(Q)) {
+    const Plan pb = make_plan_big(Q, N);
+    auto kb = cosine_topk_f32_big_kernel<4, true>;
+    IRR_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      big_smem_bytes<4>()));
+    kb<<<pb.m_tiles * pb.n_chunks, THREADS, big_smem_bytes<4>(), st>>>(
+        static_cast<const float*>(q), static_cast<const float*>(g), g_inv_norm, static_cast<int>(Q),
+        static_cast<int>(N), D, 1, pb.m_tiles, pb.n_tiles, pb.tiles_per_chunk, nullptr, nullptr,
+        q_inv_norm, out_scores);
+    IRR_LAUNCH_CHECK();
+    return IRR_OK;
+  }
   const Plan p = make_plan(Q, N);
   auto kern = cosine_topk_f32_kernel<4, true>;
   IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
