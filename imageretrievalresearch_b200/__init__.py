@@ -14,6 +14,7 @@ from .retrieval import (CapturedSearch, CosineSimilarity, DedupTopK, Gallery, Se
                         top1_top3, top1_top3_dedup, topk_hits)
 from .store import (GalleryStore, GalleryWriter, StreamedGallery, block_ranges, gather_embeddings,
                     write_gallery)
+from . import torch_ops  # registers torch.ops.irr_b200.*
 from .sharded import PeerExchange, ShardedGallery, exchange_candidates, shard_bounds
 
 __all__ = [
@@ -23,5 +24,5 @@ __all__ = [
     "CosineSimilarity", "Gallery", "TopK", "DedupTopK", "cosine_topk", "top1_top3", "topk_hits",
     "class_dedup_topk", "top1_top3_dedup", "get_fm", "cross_entropy_pair", "CEPair",
     "GalleryStore", "GalleryWriter", "StreamedGallery", "write_gallery", "gather_embeddings",
-    "block_ranges", "ShardedGallery", "PeerExchange", "CapturedSearch", "SearchPipeline", "exchange_candidates", "shard_bounds",
+    "block_ranges", "torch_ops", "ShardedGallery", "PeerExchange", "CapturedSearch", "SearchPipeline", "exchange_candidates", "shard_bounds",
 ]

@@ -631,6 +631,47 @@ def test_sharded_c_entry_single_rank():
     assert st == -4
 
 
+def test_torch_ops_match_the_python_surface_and_trace():
+    """torch.ops.irr_b200.*: same numbers as the direct calls, opcheck-clean (schema, fake kernels,
+    autograd registration), and a whole evaluation + loss step traces as ONE graph."""
+    B, D = 64, 256
+    q, p, n = synthetic.triplets(B, D, seed=5)
+    q, p, n = q.cuda(), p.cuda(), n.cuda()
+    cls = (torch.arange(B) % 8).cuda()
+    v, i = torch.ops.irr_b200.cosine_topk(q, p, 3, 1e-6, None, 0)
+    want = irr.cosine_topk(q, p, 3)
+    assert torch.equal(i, want.indices) and torch.equal(v, want.values)
+    assert torch.equal(torch.ops.irr_b200.topk_hits(i, cls, cls, 0), irr.topk_hits(i, cls, cls))
+    assert torch.equal(torch.ops.irr_b200.pair_cosine(q[:1], p, 1e-6),
+                       irr.CosineSimilarity(dim=1, eps=1e-6)(q[:1], p))
+    qa, pa, na = [t.clone().requires_grad_(True) for t in (q, p, n)]
+    losses = irr.torch_ops.triplet_losses(qa, pa, na, 0.3)
+    losses.sum().backward()
+    wl, dq, dp, dn = ref.four_losses_and_grads(q.cpu(), p.cpu(), n.cpu(), 0.3)
+    assert ((losses.detach().cpu() - wl).abs() <= LOSS_REL * wl.abs() + 1e-9).all()
+    for got, w in ((qa.grad, dq), (pa.grad, dp), (na.grad, dn)):
+        assert rel(got, w.cuda()) < GRAD_REL
+    torch.library.opcheck(torch.ops.irr_b200.cosine_topk.default, (q, p, 3, 1e-6, None, 0),
+                          test_utils=("test_schema", "test_faketensor"))
+    torch.library.opcheck(torch.ops.irr_b200.triplet_losses_fwd.default,
+                          (qa.detach().requires_grad_(True), pa.detach(), na.detach(), 0.3, 0.3, True),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+    def step(a, b, c, labels):
+        l = irr.torch_ops.triplet_losses(a, b, c, 0.3)
+        vals, idx = torch.ops.irr_b200.cosine_topk(a, b, 3, 1e-6, None, 0)
+        hits = torch.ops.irr_b200.topk_hits(idx, labels, labels, 0)
+        return l.sum(), hits.float() / a.shape[0]
+
+    traced = torch.compile(step, backend="aot_eager", fullgraph=True)
+    qa2 = q.clone().requires_grad_(True)
+    loss, frac = traced(qa2, p, n, cls)
+    loss.backward()
+    eager_loss, eager_frac = step(q, p, n, cls)
+    assert torch.equal(frac, eager_frac) and torch.equal(loss.detach(), eager_loss)
+    assert rel(qa2.grad, dq.cuda()) < GRAD_REL
+
+
 def test_dedup_edge_cases():
     # fewer distinct classes than requested, padding entries, n_distinct = 1
     idx = torch.tensor([[0, 1, 2, 3], [4, 4, 5, -1], [6, -1, -1, -1]])

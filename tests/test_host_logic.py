@@ -75,3 +75,20 @@ def test_constructor_surface_matches_reference():
         irr.CosineEmbeddingLoss(reduction="none")
     with pytest.raises(ValueError):
         irr.CosineSimilarity(dim=0)
+
+
+def test_torch_ops_are_registered_with_fake_kernels_and_no_cpu_kernel():
+    """torch.ops.irr_b200.*: schema + fake (meta) kernels give shapes / dtypes without a device, the
+    loss operator is differentiable through its registered backward, and there is no CPU kernel."""
+    m = lambda *s, dt=torch.float32: torch.empty(*s, device="meta", dtype=dt)
+    v, i = torch.ops.irr_b200.cosine_topk(m(5, 64), m(100, 64), 3, 1e-6, None, 0)
+    assert (v.shape, v.dtype, i.shape, i.dtype) == ((5, 3), torch.float32, (5, 3), torch.int64)
+    assert torch.ops.irr_b200.topk_hits(m(5, 3, dt=torch.int64), None, None, 0).shape == (2,)
+    assert torch.ops.irr_b200.pair_cosine(m(1, 64), m(100, 64), 1e-6).shape == (100,)
+    q = m(8, 64).requires_grad_(True)
+    losses = irr.torch_ops.triplet_losses(q, m(8, 64), m(8, 64), 0.3)
+    assert losses.shape == (4,) and losses.requires_grad
+    losses.sum().backward()
+    assert q.grad.shape == (8, 64)
+    with pytest.raises(NotImplementedError):
+        torch.ops.irr_b200.cosine_topk(torch.randn(5, 64), torch.randn(100, 64), 3, 1e-6, None, 0)
