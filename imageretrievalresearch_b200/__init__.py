@@ -12,7 +12,7 @@ from .losses import (ContrastiveLoss, CosineEmbeddingLoss, TripletFwdBwd, Triple
 from .producer_consumer import CEPair, cross_entropy_pair, get_fm
 from .retrieval import (CapturedSearch, CosineSimilarity, DedupTopK, Gallery, SearchPipeline, TopK, class_dedup_topk, cosine_topk,
                         top1_top3, top1_top3_dedup, topk_hits)
-from .store import (GalleryStore, GalleryWriter, StreamedGallery, block_ranges, gather_embeddings,
+from .store import (GalleryBuilder, GalleryStore, GalleryWriter, StreamedGallery, block_ranges, gather_embeddings,
                     write_gallery)
 from . import torch_ops  # registers torch.ops.irr_b200.*
 from .sharded import PeerExchange, ShardedGallery, exchange_candidates, shard_bounds
@@ -23,6 +23,6 @@ __all__ = [
     "triplet_losses", "triplet_losses_fwd_bwd",
     "CosineSimilarity", "Gallery", "TopK", "DedupTopK", "cosine_topk", "top1_top3", "topk_hits",
     "class_dedup_topk", "top1_top3_dedup", "get_fm", "cross_entropy_pair", "CEPair",
-    "GalleryStore", "GalleryWriter", "StreamedGallery", "write_gallery", "gather_embeddings",
+    "GalleryBuilder", "GalleryStore", "GalleryWriter", "StreamedGallery", "write_gallery", "gather_embeddings",
     "block_ranges", "torch_ops", "ShardedGallery", "PeerExchange", "CapturedSearch", "SearchPipeline", "exchange_candidates", "shard_bounds",
 ]

@@ -143,6 +143,68 @@ class GalleryWriter:
         self.close()
 
 
+class GalleryBuilder:
+    """A resident gallery that grows batch by batch on the device — the GPU-side form of the
+    notebook's ``fms_poss_all.append(...)`` / ``torch.cat`` accumulation
+    (inference/training_analysis.ipynb:222-231,257).  Rows land in a preallocated ``[capacity, D]``
+    buffer (doubled when full), their inverse norms are computed once as they arrive, and
+    ``gallery()`` is a zero-copy :class:`Gallery` over the rows appended so far."""
+
+    def __init__(self, dim: int, dtype: torch.dtype = torch.bfloat16, device="cuda",
+                 capacity: int = 1 << 16, eps: float = 1e-6) -> None:
+        if dtype not in _CODES:
+            raise TypeError(f"unsupported gallery dtype {dtype} (fp32 or bf16)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GalleryBuilder lives on a CUDA device (there is no CPU fallback)")
+        self.dim, self.dtype, self.eps = dim, dtype, float(eps)
+        self.rows = 0
+        self._emb = torch.empty((max(capacity, 1), dim), dtype=dtype, device=self.device)
+        self._norm = torch.empty(max(capacity, 1), dtype=torch.float32, device=self.device)
+        self._lab: Optional[torch.Tensor] = None
+
+    def _reserve(self, need: int) -> None:
+        cap = self._emb.shape[0]
+        if need <= cap:
+            return
+        while cap < need:
+            cap *= 2
+        emb = torch.empty((cap, self.dim), dtype=self.dtype, device=self.device)
+        norm = torch.empty(cap, dtype=torch.float32, device=self.device)
+        emb[: self.rows].copy_(self._emb[: self.rows])
+        norm[: self.rows].copy_(self._norm[: self.rows])
+        self._emb, self._norm = emb, norm
+        if self._lab is not None:
+            lab = torch.empty(cap, dtype=torch.int64, device=self.device)
+            lab[: self.rows].copy_(self._lab[: self.rows])
+            self._lab = lab
+
+    def append(self, embeddings: torch.Tensor, labels: Optional[torch.Tensor] = None) -> None:
+        if embeddings.dim() != 2 or embeddings.shape[1] != self.dim:
+            raise ValueError(f"expected [rows, {self.dim}] embeddings, got {tuple(embeddings.shape)}")
+        if (labels is not None) != (self._lab is not None) and self.rows > 0:
+            raise ValueError("labels must be given for every batch or for none")
+        n = embeddings.shape[0]
+        self._reserve(self.rows + n)
+        dst = self._emb[self.rows: self.rows + n]
+        dst.copy_(embeddings.detach())                      # converts dtype / device as needed
+        self._norm[self.rows: self.rows + n].copy_(_ops.row_inv_norms(dst, self.eps))
+        if labels is not None:
+            if self._lab is None:
+                self._lab = torch.empty(self._emb.shape[0], dtype=torch.int64, device=self.device)
+            self._lab[self.rows: self.rows + n].copy_(labels.detach().reshape(-1))
+        self.rows += n
+
+    @property
+    def labels(self) -> Optional[torch.Tensor]:
+        return None if self._lab is None else self._lab[: self.rows]
+
+    def gallery(self, first_row: int = 0) -> Gallery:
+        g = Gallery(self._emb[: self.rows], eps=self.eps, first_row=first_row, cache_norms=False)
+        g.inv_norm = self._norm[: self.rows]
+        return g
+
+
 def write_gallery(path: Union[str, os.PathLike], embeddings: torch.Tensor,
                   labels: Optional[torch.Tensor] = None, eps: float = 1e-6,
                   chunk_rows: int = 1 << 16) -> None:

@@ -132,3 +132,27 @@ def test_store_load_stream_and_labels_on_device(tmp_path):
     assert torch.equal(r.indices, full.indices + 10_000)
     hits = irr.topk_hits(want.indices, lab[planted[:, 0]].cuda(), s.labels().cuda())
     assert hits.tolist() == [Q, Q]
+
+
+@pytest.mark.gpu
+def test_gallery_builder_grows_and_matches_one_shot():
+    N, D, Q, k = 5_000, 256, 40, 3
+    q, gal = synthetic.tied_gallery(N, D, Q, dtype=torch.bfloat16)
+    lab = torch.arange(N) % 13
+    b = irr.GalleryBuilder(D, torch.bfloat16, "cuda", capacity=64)          # forces several regrowths
+    for lo, hi in irr.block_ranges(N, 777):
+        b.append(gal[lo:hi].cuda() if lo % 2 else gal[lo:hi], lab[lo:hi])   # device and host batches
+        if hi == 1554:                                                     # searchable while growing
+            part = b.gallery().search(q.cuda(), k)
+            want = irr.cosine_topk(q.cuda(), gal[:hi].cuda(), k)
+            assert torch.equal(part.indices, want.indices) and torch.equal(part.values, want.values)
+    full = irr.Gallery(gal.cuda())
+    got, want = b.gallery().search(q.cuda(), k), full.search(q.cuda(), k)
+    assert b.rows == N and torch.equal(b.labels.cpu(), lab)
+    assert torch.equal(got.indices, want.indices) and torch.equal(got.values, want.values)
+    assert torch.equal(b.gallery().inv_norm, full.inv_norm)
+
+
+def test_gallery_builder_needs_cuda():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        irr.GalleryBuilder(64, torch.float32, "cpu")
