@@ -144,7 +144,7 @@ def test_gallery_builder_grows_and_matches_one_shot():
         b.append(gal[lo:hi].cuda() if lo % 2 else gal[lo:hi], lab[lo:hi])   # device and host batches
         if hi == 1554:                                                     # searchable while growing
             part = b.gallery().search(q.cuda(), k)
-            want = irr.cosine_topk(q.cuda(), gal[:hi].cuda(), k)
+            want = irr.Gallery(gal[:hi].cuda()).search(q.cuda(), k)       # same cached-norm path
             assert torch.equal(part.indices, want.indices) and torch.equal(part.values, want.values)
     full = irr.Gallery(gal.cuda())
     got, want = b.gallery().search(q.cuda(), k), full.search(q.cuda(), k)
