@@ -79,10 +79,13 @@ class ClockSampler:
                0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks", 0x100: "display",
                0x10: "sync_boost"}
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
+        if not enabled:            # only rank 0 polls NVML: eight pollers on one box perturb the
+            self.nv, self.err = None, "not sampled on this rank"   # launches they are meant to observe
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -106,7 +109,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.005)
+            self._stop.wait(0.010)
 
     def __enter__(self):
         if self.nv:
@@ -255,7 +258,7 @@ def run_b200(a):
         s.record(); e.record()
     barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=(rank == 0)) as clocks:
         start.record()
         for s, e in kev:
             lib.irr_profile_next_topk(s.cuda_event, e.cuda_event)
