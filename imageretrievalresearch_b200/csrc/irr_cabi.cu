@@ -225,9 +225,11 @@ irr_status irr_topk_exchange_merge(const float* local_val, const int64_t* local_
   if (G < 1 || G > IRR_MAX_PEERS || rank < 0 || rank >= G || Q < 0 || k < 1 || !peer_bufs)
     return IRR_ERR_INVALID_ARG;
   if (k > IRR_MAX_K) return IRR_ERR_K_TOO_LARGE;
-  if (mode != IRR_XCHG_FUSED && mode != IRR_XCHG_PUSH && mode != IRR_XCHG_MERGE)
+  if (mode != IRR_XCHG_FUSED && mode != IRR_XCHG_PUSH && mode != IRR_XCHG_MERGE &&
+      mode != IRR_XCHG_MERGE_PREV)
     return IRR_ERR_INVALID_ARG;
-  if (mode != IRR_XCHG_MERGE && Q > 0 && (!local_val || !local_idx)) return IRR_ERR_INVALID_ARG;
+  if ((mode == IRR_XCHG_FUSED || mode == IRR_XCHG_PUSH) && Q > 0 && (!local_val || !local_idx))
+    return IRR_ERR_INVALID_ARG;
   if (mode != IRR_XCHG_PUSH && Q > 0 && (!out_val || !out_idx)) return IRR_ERR_INVALID_ARG;
   return topk_exchange_merge(local_val, local_idx, peer_bufs, G, rank, Q, k, buf_bytes, mode,
                              out_val, out_idx, reinterpret_cast<cudaStream_t>(stream));

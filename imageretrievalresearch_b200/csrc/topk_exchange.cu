@@ -16,10 +16,13 @@
 // Buffer layout (irr_topk_exchange_bytes):
 //   [0,   64)  uint32 flag[g]  = last epoch whose list rank g finished storing into THIS buffer
 //   [256, 264) uint32 epoch (calls completed by the owner), uint32 done (CTAs that finished pushing)
-//   [512, ..)  two parity halves; half (epoch & 1) holds G slots [scores Q*k fp32 | pad | indices Q*k i64]
-// Why two halves are enough: a rank can enter call n+2 (which overwrites the half call n used) only
-// after it left call n+1, i.e. after every peer published epoch n+1, and a peer publishes n+1 only
-// after its call n — including the merge that read half n&1 — has completed in stream order.
+//   [512, ..)  three parts; part (epoch % 3) holds G slots [scores Q*k fp32 | pad | indices Q*k i64]
+// Why the parts are never overwritten while still being read.  Fused calls (push n, merge n): a
+// rank pushes n+2 only after its merge n+1, i.e. after every peer pushed n+1, which every peer does
+// after its own merge n — two parts would do.  Lagged calls (per search: merge n-1, THEN push n —
+// the merge refers to the previous search, so a rank is never held up by peers that are less than
+// one search behind): a rank pushes n+2 after its merge n, i.e. after every peer pushed n, which
+// every peer does after its merge n-1 — so part (n+2) % 3 == (n-1) % 3 is free everywhere.
 //
 // Deadlock freedom: a CTA only ever waits for REMOTE pushes; a push waits for nothing.  The fused
 // kernel keeps its grid small enough (<= 2 CTAs per SM) to be co-resident, so the push of a rank is
@@ -35,7 +38,8 @@ namespace {
 constexpr int XT = 256;          // threads per CTA
 constexpr int XW = XT / 32;      // query rows merged per CTA iteration
 constexpr size_t X_STATE = 256;  // byte offset of {epoch, done}
-constexpr size_t X_DATA = 512;   // byte offset of the first parity half
+constexpr size_t X_DATA = 512;   // byte offset of the first epoch part
+constexpr uint32_t X_PARTS = 3;
 
 struct Peers {
   uint8_t* p[IRR_MAX_PEERS];
@@ -45,7 +49,7 @@ struct XGeom {
   size_t n;           // Q*k
   size_t idx_off;     // bytes from slot start to the int64 indices
   size_t slot_bytes;
-  size_t half_bytes;  // distance between the two parity halves
+  size_t half_bytes;  // distance between the three epoch parts
 };
 
 XGeom make_geom(int32_t G, int64_t Q, int32_t k, size_t buf_bytes) {
@@ -53,7 +57,7 @@ XGeom make_geom(int32_t G, int64_t Q, int32_t k, size_t buf_bytes) {
   x.n = static_cast<size_t>(Q) * k;
   x.idx_off = align_up(x.n * 4, 16);
   x.slot_bytes = x.idx_off + align_up(x.n * 8, 16);
-  x.half_bytes = buf_bytes ? (buf_bytes - X_DATA) / 2 / 256 * 256
+  x.half_bytes = buf_bytes ? (buf_bytes - X_DATA) / X_PARTS / 256 * 256
                            : align_up(static_cast<size_t>(G) * x.slot_bytes, 256);
   return x;
 }
@@ -72,7 +76,7 @@ __device__ __forceinline__ void push_phase(const float* __restrict__ lv,
                                            const int64_t* __restrict__ li, const Peers& peers, int G,
                                            int rank, const XGeom& x, uint32_t epoch,
                                            uint32_t* state) {
-  const size_t slot = X_DATA + (epoch & 1u) * x.half_bytes + static_cast<size_t>(rank) * x.slot_bytes;
+  const size_t slot = X_DATA + (epoch % X_PARTS) * x.half_bytes + static_cast<size_t>(rank) * x.slot_bytes;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < x.n; e += stride) {
     const float v = lv[e];
@@ -134,7 +138,7 @@ __device__ __forceinline__ void merge_phase(const uint8_t* mine, int G, int64_t 
                                             float* __restrict__ out_val,
                                             int64_t* __restrict__ out_idx) {
   const int lane = threadIdx.x & 31;
-  const uint8_t* half = mine + X_DATA + (epoch & 1u) * x.half_bytes;
+  const uint8_t* half = mine + X_DATA + (epoch % X_PARTS) * x.half_bytes;
   const int total = G * k;
   for (int64_t qi = static_cast<int64_t>(blockIdx.x) * XW + (threadIdx.x >> 5); qi < Q;
        qi += static_cast<int64_t>(gridDim.x) * XW) {
@@ -157,7 +161,8 @@ __device__ __forceinline__ void merge_phase(const uint8_t* mine, int G, int64_t 
   }
 }
 
-// mode: IRR_XCHG_FUSED = push + wait + merge, IRR_XCHG_MERGE = wait + merge of the epoch already pushed
+// mode: IRR_XCHG_FUSED = push + wait + merge, IRR_XCHG_MERGE = wait + merge of the epoch already
+// pushed, IRR_XCHG_MERGE_PREV = wait + merge of the epoch BEFORE the one last pushed
 template <int KMAX>
 __global__ void __launch_bounds__(XT)
 exchange_merge_kernel(const float* __restrict__ lv, const int64_t* __restrict__ li,
@@ -171,6 +176,8 @@ exchange_merge_kernel(const float* __restrict__ lv, const int64_t* __restrict__ 
   if (mode == IRR_XCHG_FUSED) {
     ++epoch;
     push_phase(lv, li, peers, G, rank, x, epoch, state);
+  } else if (mode == IRR_XCHG_MERGE_PREV) {
+    --epoch;
   }
   wait_phase(mine, G, epoch, timeout_ns);
   merge_phase<KMAX>(mine, G, Q, k, x, epoch, out_val, out_idx);
@@ -207,7 +214,7 @@ unsigned long long exchange_timeout_ns() {
 
 size_t topk_exchange_bytes(int32_t G, int64_t Q, int32_t k) {
   const XGeom x = make_geom(G, Q, k, 0);
-  return X_DATA + 2 * x.half_bytes;
+  return X_DATA + X_PARTS * x.half_bytes;
 }
 
 irr_status topk_exchange_merge(const float* local_val, const int64_t* local_idx,
@@ -233,11 +240,12 @@ irr_status topk_exchange_merge(const float* local_val, const int64_t* local_idx,
     if (mode == IRR_XCHG_PUSH) return IRR_OK;
   }
   if (k > IRR_MAX_K_FUSED) {
+    if (mode == IRR_XCHG_MERGE_PREV) return IRR_ERR_K_TOO_LARGE;   // lagged merges: fused-k lists only
     // large k: the sorted-merge kernel runs one CTA per query (not co-resident), so the wait is a
     // separate one-warp kernel in front of it; the merge reads the lists in place
     exchange_wait_kernel<<<1, 32, 0, st>>>(peers.p[rank], G, tmo);
     IRR_LAUNCH_CHECK();
-    // which half holds the lists depends on the epoch in device memory: the merge reads it itself
+    // which part holds the lists depends on the epoch in device memory: the merge reads it itself
     return merge_candidates_large_exchange(peers.p[rank], X_STATE, X_DATA, x.half_bytes,
                                            x.slot_bytes, x.idx_off, G, Q, k, out_val, out_idx, st);
   }

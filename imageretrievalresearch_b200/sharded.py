@@ -157,6 +157,20 @@ class PeerExchange:
         return _ops.topk_exchange_merge(vals, idx, self.ptrs, self.rank, Q, k, self.nbytes,
                                         _lib.IRR_XCHG_FUSED, self.device, out)
 
+    # lagged exchange: per search "merge_prev() then push()", flush with merge_current()
+    def push(self, vals: torch.Tensor, idx: torch.Tensor) -> None:
+        Q, k = vals.shape
+        _ops.topk_exchange_merge(vals, idx, self.ptrs, self.rank, Q, k, self.nbytes,
+                                 _lib.IRR_XCHG_PUSH, self.device)
+
+    def merge_prev(self, Q: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        return _ops.topk_exchange_merge(None, None, self.ptrs, self.rank, Q, k, self.nbytes,
+                                        _lib.IRR_XCHG_MERGE_PREV, self.device)
+
+    def merge_current(self, Q: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        return _ops.topk_exchange_merge(None, None, self.ptrs, self.rank, Q, k, self.nbytes,
+                                        _lib.IRR_XCHG_MERGE, self.device)
+
     def close(self) -> None:
         """Collective: no rank may still be storing into a buffer that is about to be unmapped."""
         torch.cuda.synchronize(self.device)
@@ -194,6 +208,7 @@ class ShardedGallery:
         self._peer: Optional[PeerExchange] = None
         self._peer_failed = False
         self.exchange_error: Optional[str] = None
+        self._lagged: Optional[Tuple[int, int]] = None   # (Q, k) of the search whose result is pending
         lo, hi = shard_bounds(total_rows, self.world, self.rank)
         if local_embeddings.shape[0] != hi - lo:
             raise ValueError(
@@ -263,9 +278,53 @@ class ShardedGallery:
         return CapturedSearch(lambda q, kk: self.search(q, kk), num_queries, emb.shape[1], k,
                               emb.dtype, emb.device)
 
+    def search_lagged(self, queries: torch.Tensor, k: int) -> Optional[TopK]:
+        """A stream of searches with one search of slack between the ranks.  Enqueues this
+        search (local top-k + push of its lists to every peer) and returns the merged result of
+        the PREVIOUS ``search_lagged`` call (None on the first call); :meth:`flush` collects the
+        last one.  ``search`` ends every call in a rendezvous, so every step costs the slowest of
+        G kernels; here the rendezvous is with the peers' previous push, which has long happened
+        unless a peer is more than one whole search behind.  Same results as ``search``, one call
+        later.  Needs the peer-memory exchange, k <= 16, and the same (Q, k) from call to call."""
+        if k > self.total_rows:
+            raise RuntimeError("selected index k out of range")
+        Q = queries.shape[0]
+        if self.world == 1:
+            prev, self._lagged_single = getattr(self, "_lagged_single", None), \
+                self.local.search(queries, k, allow_short=True)
+            return prev
+        if k > _lib.IRR_MAX_K_FUSED:
+            raise ValueError("search_lagged supports k <= 16")
+        if self._lagged is not None and self._lagged != (Q, k):
+            raise ValueError("search_lagged needs the same (Q, k) from call to call; flush() first")
+        peer = self._peer_exchange(Q, k)
+        if peer is None:
+            raise RuntimeError("search_lagged needs the peer-memory exchange; unavailable: "
+                               f"{self.exchange_error}")
+        lv, li = self.local.search(queries, k, allow_short=True)
+        prev = None
+        if self._lagged is not None:
+            prev = TopK(*peer.merge_prev(Q, k))      # merge n-1 BEFORE push n (see topk_exchange.cu)
+        peer.push(lv, li)
+        self._lagged = (Q, k)
+        return prev
+
+    def flush(self) -> Optional[TopK]:
+        """The result of the last :meth:`search_lagged` call (None if there is none pending)."""
+        if self.world == 1:
+            prev, self._lagged_single = getattr(self, "_lagged_single", None), None
+            return prev
+        if self._lagged is None:
+            return None
+        Q, k = self._lagged
+        self._lagged = None
+        return TopK(*self._peer.merge_current(Q, k))
+
     def search(self, queries: torch.Tensor, k: int) -> TopK:
         if k > self.total_rows:
             raise RuntimeError("selected index k out of range")
+        if self._lagged is not None:
+            raise RuntimeError("a lagged search is pending: flush() before a plain search")
         if self.world == 1:
             return self.local.search(queries, k, allow_short=True)
         peer = self._peer_exchange(queries.shape[0], k)

@@ -74,6 +74,24 @@ def main():
                       f"Q={Q} k={k} {dt} transport={sg.transport}; tie row -> "
                       f"{gots[0].indices[0, :2].tolist()}", flush=True)
             ok &= bool(flag.item())
+            if exchange == "peer" and k <= 16:
+                # lagged stream: same results, one call late; ranks deliberately out of step
+                outs = []
+                for j, q in enumerate(qs):
+                    if rank == j % world:
+                        torch.cuda._sleep(20_000_000)      # ~10 ms: this rank falls behind
+                    r = sg.search_lagged(q, k)
+                    if r is not None:
+                        outs.append(r)
+                outs.append(sg.flush())
+                same = all(torch.equal(o.indices, g.indices) and torch.equal(o.values, g.values)
+                           for o, g in zip(outs, gots)) and len(outs) == len(gots)
+                flag = torch.tensor([1 if same else 0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if rank == 0:
+                    print(f"[{'PASS' if flag.item() else 'FAIL'}] {name} x{world} lagged stream == plain "
+                          f"search: N={N} Q={Q} k={k}", flush=True)
+                ok &= bool(flag.item())
             sg.close()
         if try_ok:
             usable.append((exchange, mapping))

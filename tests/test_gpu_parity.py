@@ -538,7 +538,7 @@ def test_peer_exchange_protocol_on_one_device(G, Q, k, monkeypatch):
     from imageretrievalresearch_b200 import _lib
     monkeypatch.setenv("IRR_EXCHANGE_TIMEOUT_MS", "2000")   # a protocol bug traps instead of hanging
     dev = torch.device("cuda", 0)
-    nbytes = _ops.topk_exchange_bytes(G, Q, k) + 4096       # not the exact size: halves must adapt
+    nbytes = _ops.topk_exchange_bytes(G, Q, k) + 4096       # not the exact size: parts must adapt
     bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(G)]
     ptrs = [b.data_ptr() for b in bufs]
     for rnd in range(3):
@@ -562,6 +562,38 @@ def test_peer_exchange_protocol_on_one_device(G, Q, k, monkeypatch):
             assert torch.equal(i.cpu(), wi) and torch.equal(v.cpu(), wv), (rnd, r)
     epochs = [int(b[256:260].view(torch.int32).item()) for b in bufs]
     assert epochs == [3] * G
+
+
+@pytest.mark.parametrize("G,Q,k", [(4, 21, 3), (8, 300, 10), (2, 5, 1)])
+def test_peer_exchange_lagged_protocol_on_one_device(G, Q, k, monkeypatch):
+    """Lagged exchange (per search: MERGE_PREV of search n-1, then PUSH of search n; MERGE at the
+    end) with G virtual ranks on one device over seven searches: every rank gets every search's
+    merged list, one call late, and the three buffer parts rotate without clobbering."""
+    from imageretrievalresearch_b200 import _lib
+    monkeypatch.setenv("IRR_EXCHANGE_TIMEOUT_MS", "2000")
+    dev = torch.device("cuda", 0)
+    nbytes = _ops.topk_exchange_bytes(G, Q, k)
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(G)]
+    ptrs = [b.data_ptr() for b in bufs]
+    rounds = []
+    for n in range(7):
+        torch.manual_seed(77 * n + G + k)
+        vals = torch.randn(G, Q, k).sort(dim=2, descending=True).values
+        idx = torch.stack([torch.randperm(5000)[:k].sort().values + g * 5000
+                           for g in range(G) for _ in range(Q)]).view(G, Q, k)
+        rounds.append((vals, idx))
+        dv, di = vals.cuda(), idx.cuda()
+        for r in range(G):
+            if n > 0:
+                v, i = _ops.topk_exchange_merge(None, None, ptrs, r, Q, k, nbytes,
+                                                _lib.IRR_XCHG_MERGE_PREV, dev)
+                wv, wi = ref.merge_candidates(*rounds[n - 1], k)
+                assert torch.equal(i.cpu(), wi) and torch.equal(v.cpu(), wv), (n, r)
+            _ops.topk_exchange_merge(dv[r], di[r], ptrs, r, Q, k, nbytes, _lib.IRR_XCHG_PUSH, dev)
+    wv, wi = ref.merge_candidates(*rounds[-1], k)
+    for r in range(G):
+        v, i = _ops.topk_exchange_merge(None, None, ptrs, r, Q, k, nbytes, _lib.IRR_XCHG_MERGE, dev)
+        assert torch.equal(i.cpu(), wi) and torch.equal(v.cpu(), wv), r
 
 
 @pytest.mark.parametrize("Q,k,dtype", [(1, 3, torch.bfloat16), (64, 10, torch.bfloat16),
