@@ -17,7 +17,7 @@ IRR_MAX_K_FUSED = 16
 IRR_ROW_STATS = 8
 IRR_LOSS_COSINE_EMBEDDING, IRR_LOSS_CONTRASTIVE = 1, 2
 IRR_MAX_PEERS = 16
-IRR_XCHG_FUSED, IRR_XCHG_PUSH, IRR_XCHG_MERGE, IRR_XCHG_MERGE_PREV = 0, 1, 2, 3
+IRR_XCHG_FUSED, IRR_XCHG_PUSH, IRR_XCHG_MERGE = 0, 1, 2
 
 _i32, _i64, _f32, _sz, _vp = C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_void_p
 

@@ -225,8 +225,7 @@ irr_status irr_topk_exchange_merge(const float* local_val, const int64_t* local_
   if (G < 1 || G > IRR_MAX_PEERS || rank < 0 || rank >= G || Q < 0 || k < 1 || !peer_bufs)
     return IRR_ERR_INVALID_ARG;
   if (k > IRR_MAX_K) return IRR_ERR_K_TOO_LARGE;
-  if (mode != IRR_XCHG_FUSED && mode != IRR_XCHG_PUSH && mode != IRR_XCHG_MERGE &&
-      mode != IRR_XCHG_MERGE_PREV)
+  if (mode != IRR_XCHG_FUSED && mode != IRR_XCHG_PUSH && mode != IRR_XCHG_MERGE)
     return IRR_ERR_INVALID_ARG;
   if ((mode == IRR_XCHG_FUSED || mode == IRR_XCHG_PUSH) && Q > 0 && (!local_val || !local_idx))
     return IRR_ERR_INVALID_ARG;

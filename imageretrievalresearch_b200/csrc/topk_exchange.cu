@@ -16,13 +16,14 @@
 // Buffer layout (irr_topk_exchange_bytes):
 //   [0,   64)  uint32 flag[g]  = last epoch whose list rank g finished storing into THIS buffer
 //   [256, 264) uint32 epoch (calls completed by the owner), uint32 done (CTAs that finished pushing)
-//   [512, ..)  three parts; part (epoch % 3) holds G slots [scores Q*k fp32 | pad | indices Q*k i64]
-// Why the parts are never overwritten while still being read.  Fused calls (push n, merge n): a
-// rank pushes n+2 only after its merge n+1, i.e. after every peer pushed n+1, which every peer does
-// after its own merge n — two parts would do.  Lagged calls (per search: merge n-1, THEN push n —
-// the merge refers to the previous search, so a rank is never held up by peers that are less than
-// one search behind): a rank pushes n+2 after its merge n, i.e. after every peer pushed n, which
-// every peer does after its merge n-1 — so part (n+2) % 3 == (n-1) % 3 is free everywhere.
+//   [512, ..)  two parity halves; half (epoch & 1) holds G slots [scores Q*k fp32 | pad | indices Q*k i64]
+// Why two halves are enough, for both call orders the library uses.  Fused calls (push n, merge n):
+// a rank pushes n+2 (overwriting the half call n used) only after its merge n+1, i.e. after every
+// peer pushed n+1, which every peer does after its own merge n.  Lagged calls (per search: merge
+// n-1, THEN push n — the rendezvous of a search is with the peers' PREVIOUS push, so a rank is
+// never held up by peers that are less than one search behind): a rank pushes n+1 (overwriting the
+// half of n-1) only after its merge n, i.e. after every peer pushed n, which every peer does after
+// its own merge n-1.
 //
 // Deadlock freedom: a CTA only ever waits for REMOTE pushes; a push waits for nothing.  The fused
 // kernel keeps its grid small enough (<= 2 CTAs per SM) to be co-resident, so the push of a rank is
@@ -38,8 +39,8 @@ namespace {
 constexpr int XT = 256;          // threads per CTA
 constexpr int XW = XT / 32;      // query rows merged per CTA iteration
 constexpr size_t X_STATE = 256;  // byte offset of {epoch, done}
-constexpr size_t X_DATA = 512;   // byte offset of the first epoch part
-constexpr uint32_t X_PARTS = 3;
+constexpr size_t X_DATA = 512;   // byte offset of the first parity half
+constexpr uint32_t X_PARTS = 2;
 
 struct Peers {
   uint8_t* p[IRR_MAX_PEERS];
@@ -49,7 +50,7 @@ struct XGeom {
   size_t n;           // Q*k
   size_t idx_off;     // bytes from slot start to the int64 indices
   size_t slot_bytes;
-  size_t half_bytes;  // distance between the three epoch parts
+  size_t half_bytes;  // distance between the two parity halves
 };
 
 XGeom make_geom(int32_t G, int64_t Q, int32_t k, size_t buf_bytes) {
@@ -161,8 +162,7 @@ __device__ __forceinline__ void merge_phase(const uint8_t* mine, int G, int64_t 
   }
 }
 
-// mode: IRR_XCHG_FUSED = push + wait + merge, IRR_XCHG_MERGE = wait + merge of the epoch already
-// pushed, IRR_XCHG_MERGE_PREV = wait + merge of the epoch BEFORE the one last pushed
+// mode: IRR_XCHG_FUSED = push + wait + merge, IRR_XCHG_MERGE = wait + merge of the epoch already pushed
 template <int KMAX>
 __global__ void __launch_bounds__(XT)
 exchange_merge_kernel(const float* __restrict__ lv, const int64_t* __restrict__ li,
@@ -176,8 +176,6 @@ exchange_merge_kernel(const float* __restrict__ lv, const int64_t* __restrict__ 
   if (mode == IRR_XCHG_FUSED) {
     ++epoch;
     push_phase(lv, li, peers, G, rank, x, epoch, state);
-  } else if (mode == IRR_XCHG_MERGE_PREV) {
-    --epoch;
   }
   wait_phase(mine, G, epoch, timeout_ns);
   merge_phase<KMAX>(mine, G, Q, k, x, epoch, out_val, out_idx);
@@ -240,7 +238,6 @@ irr_status topk_exchange_merge(const float* local_val, const int64_t* local_idx,
     if (mode == IRR_XCHG_PUSH) return IRR_OK;
   }
   if (k > IRR_MAX_K_FUSED) {
-    if (mode == IRR_XCHG_MERGE_PREV) return IRR_ERR_K_TOO_LARGE;   // lagged merges: fused-k lists only
     // large k: the sorted-merge kernel runs one CTA per query (not co-resident), so the wait is a
     // separate one-warp kernel in front of it; the merge reads the lists in place
     exchange_wait_kernel<<<1, 32, 0, st>>>(peers.p[rank], G, tmo);

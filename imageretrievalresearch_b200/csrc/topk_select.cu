@@ -106,8 +106,8 @@ merge_large_kernel(const float* __restrict__ cand_val, int64_t val_rank_stride,
   __shared__ float sv[MRG_SLOTS];
   __shared__ long long si[MRG_SLOTS];
   if (epoch_word) {
-    // lists sit in a peer-exchange buffer (topk_exchange.cu): part (epoch % 3) of three
-    const int64_t off = static_cast<int64_t>(__ldg(epoch_word) % 3u) * half_bytes;
+    // lists sit in a peer-exchange buffer (topk_exchange.cu): odd epochs use the second half
+    const int64_t off = static_cast<int64_t>(__ldg(epoch_word) & 1u) * half_bytes;
     cand_val = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(cand_val) + off);
     cand_idx = reinterpret_cast<const int64_t*>(reinterpret_cast<const uint8_t*>(cand_idx) + off);
   }

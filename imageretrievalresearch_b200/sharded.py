@@ -157,17 +157,15 @@ class PeerExchange:
         return _ops.topk_exchange_merge(vals, idx, self.ptrs, self.rank, Q, k, self.nbytes,
                                         _lib.IRR_XCHG_FUSED, self.device, out)
 
-    # lagged exchange: per search "merge_prev() then push()", flush with merge_current()
+    # lagged exchange: per search "merge_pushed() (the previous search) then push()"; the last
+    # search of a stream is collected with one more merge_pushed()
     def push(self, vals: torch.Tensor, idx: torch.Tensor) -> None:
         Q, k = vals.shape
         _ops.topk_exchange_merge(vals, idx, self.ptrs, self.rank, Q, k, self.nbytes,
                                  _lib.IRR_XCHG_PUSH, self.device)
 
-    def merge_prev(self, Q: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        return _ops.topk_exchange_merge(None, None, self.ptrs, self.rank, Q, k, self.nbytes,
-                                        _lib.IRR_XCHG_MERGE_PREV, self.device)
-
-    def merge_current(self, Q: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    def merge_pushed(self, Q: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Wait for and merge the G lists of the epoch this rank pushed last."""
         return _ops.topk_exchange_merge(None, None, self.ptrs, self.rank, Q, k, self.nbytes,
                                         _lib.IRR_XCHG_MERGE, self.device)
 
@@ -304,7 +302,7 @@ class ShardedGallery:
         lv, li = self.local.search(queries, k, allow_short=True)
         prev = None
         if self._lagged is not None:
-            prev = TopK(*peer.merge_prev(Q, k))      # merge n-1 BEFORE push n (see topk_exchange.cu)
+            prev = TopK(*peer.merge_pushed(Q, k))    # merge n-1 BEFORE push n (see topk_exchange.cu)
         peer.push(lv, li)
         self._lagged = (Q, k)
         return prev
@@ -318,7 +316,7 @@ class ShardedGallery:
             return None
         Q, k = self._lagged
         self._lagged = None
-        return TopK(*self._peer.merge_current(Q, k))
+        return TopK(*self._peer.merge_pushed(Q, k))
 
     def search(self, queries: torch.Tensor, k: int) -> TopK:
         if k > self.total_rows:

@@ -152,16 +152,14 @@ IRR_API irr_status irr_topk_merge_strided(const float* cand_val, int64_t val_ran
  * buffer, so the launch is CUDA-graph capturable.  G <= IRR_MAX_PEERS.
  * mode: IRR_XCHG_FUSED the call described above; IRR_XCHG_PUSH store + publish only;
  *       IRR_XCHG_MERGE wait + merge of the epoch last pushed (PUSH then MERGE == FUSED; used to
- *       stage the protocol, e.g. several virtual ranks on one device in the tests);
- *       IRR_XCHG_MERGE_PREV wait + merge of the epoch BEFORE the one last pushed (k <= 16).  A
- *       stream of searches issued as "MERGE_PREV (result of search n-1), then PUSH (lists of
+ *       stage the protocol, e.g. several virtual ranks on one device in the tests).
+ *       A stream of searches issued as "MERGE (result of search n-1), then PUSH (lists of
  *       search n)" never makes a rank wait for a peer that is less than one search behind: the
  *       rendezvous of every search is with the peers' PREVIOUS push (lagged exchange; the last
- *       search of the stream is collected with MERGE).  Do not mix FUSED and lagged calls
- *       without a MERGE in between.
+ *       search of the stream is collected with one more MERGE).
  * ------------------------------------------------------------------------------------------ */
 #define IRR_MAX_PEERS 16
-enum { IRR_XCHG_FUSED = 0, IRR_XCHG_PUSH = 1, IRR_XCHG_MERGE = 2, IRR_XCHG_MERGE_PREV = 3 };
+enum { IRR_XCHG_FUSED = 0, IRR_XCHG_PUSH = 1, IRR_XCHG_MERGE = 2 };
 IRR_API size_t irr_topk_exchange_bytes(int32_t G, int64_t Q, int32_t k);
 IRR_API irr_status irr_topk_exchange_merge(const float* local_val, const int64_t* local_idx,
                                            void* const* peer_bufs, int32_t G, int32_t rank,

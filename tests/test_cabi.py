@@ -94,9 +94,9 @@ def test_exchange_entry_points_validate_without_a_device():
     lib = _lib.load()
     buf = C.create_string_buffer(4096)
     p16 = (C.addressof(buf) + 15) // 16 * 16
-    # layout: header + three epoch parts of G slots [fp32 Q*k | pad16 | int64 Q*k]
-    assert lib.irr_topk_exchange_bytes(8, 4096, 3) == 512 + 3 * 8 * (4096 * 3 * 12)
-    assert lib.irr_topk_exchange_bytes(2, 1, 1) >= 512 + 3 * 2 * 32
+    # layout: header + two halves of G slots [fp32 Q*k | pad16 | int64 Q*k]
+    assert lib.irr_topk_exchange_bytes(8, 4096, 3) == 512 + 2 * 8 * (4096 * 3 * 12)
+    assert lib.irr_topk_exchange_bytes(2, 1, 1) >= 512 + 2 * 2 * 32
     assert lib.irr_topk_exchange_bytes(17, 1, 1) == 0          # > IRR_MAX_PEERS
     assert lib.irr_topk_exchange_bytes(0, 1, 1) == 0
     assert int(re.search(r"#define IRR_MAX_PEERS (\d+)", HEADER).group(1)) == _lib.IRR_MAX_PEERS

@@ -538,7 +538,7 @@ def test_peer_exchange_protocol_on_one_device(G, Q, k, monkeypatch):
     from imageretrievalresearch_b200 import _lib
     monkeypatch.setenv("IRR_EXCHANGE_TIMEOUT_MS", "2000")   # a protocol bug traps instead of hanging
     dev = torch.device("cuda", 0)
-    nbytes = _ops.topk_exchange_bytes(G, Q, k) + 4096       # not the exact size: parts must adapt
+    nbytes = _ops.topk_exchange_bytes(G, Q, k) + 4096       # not the exact size: halves must adapt
     bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(G)]
     ptrs = [b.data_ptr() for b in bufs]
     for rnd in range(3):
@@ -566,9 +566,9 @@ def test_peer_exchange_protocol_on_one_device(G, Q, k, monkeypatch):
 
 @pytest.mark.parametrize("G,Q,k", [(4, 21, 3), (8, 300, 10), (2, 5, 1)])
 def test_peer_exchange_lagged_protocol_on_one_device(G, Q, k, monkeypatch):
-    """Lagged exchange (per search: MERGE_PREV of search n-1, then PUSH of search n; MERGE at the
-    end) with G virtual ranks on one device over seven searches: every rank gets every search's
-    merged list, one call late, and the three buffer parts rotate without clobbering."""
+    """Lagged exchange (per search: MERGE of search n-1, then PUSH of search n; one more MERGE at
+    the end) with G virtual ranks on one device over seven searches: every rank gets every
+    search's merged list, one call late, and the two buffer halves rotate without clobbering."""
     from imageretrievalresearch_b200 import _lib
     monkeypatch.setenv("IRR_EXCHANGE_TIMEOUT_MS", "2000")
     dev = torch.device("cuda", 0)
@@ -586,7 +586,7 @@ def test_peer_exchange_lagged_protocol_on_one_device(G, Q, k, monkeypatch):
         for r in range(G):
             if n > 0:
                 v, i = _ops.topk_exchange_merge(None, None, ptrs, r, Q, k, nbytes,
-                                                _lib.IRR_XCHG_MERGE_PREV, dev)
+                                                _lib.IRR_XCHG_MERGE, dev)
                 wv, wi = ref.merge_candidates(*rounds[n - 1], k)
                 assert torch.equal(i.cpu(), wi) and torch.equal(v.cpu(), wv), (n, r)
             _ops.topk_exchange_merge(dv[r], di[r], ptrs, r, Q, k, nbytes, _lib.IRR_XCHG_PUSH, dev)
