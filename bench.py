@@ -368,9 +368,10 @@ def run_b200(a):
         dist.barrier()
 
     if rank == 0:
-        # top-k (gallery norms produced inside it), partial merge (+ exchange/merge); 257..512 queries
+        # top-k (gallery norms produced inside it), partial merge (+ the fused exchange/merge kernel, or
+        # the lagged pair merge-of-previous + push); 257..512 queries
         # without cached norms still run the streaming norm pre-pass kernel
-        launches_per_step = 2 + (1 if 256 < Q <= 512 else 0) + (1 if world > 1 else 0)
+        launches_per_step = 2 + (1 if 256 < Q <= 512 else 0) + ((2 if lagged else 1) if world > 1 else 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
