@@ -92,3 +92,14 @@ def test_torch_ops_are_registered_with_fake_kernels_and_no_cpu_kernel():
     assert q.grad.shape == (8, 64)
     with pytest.raises(NotImplementedError):
         torch.ops.irr_b200.cosine_topk(torch.randn(5, 64), torch.randn(100, 64), 3, 1e-6, None, 0)
+
+
+def test_serving_helpers_refuse_the_cpu():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        irr.SearchPipeline(lambda q, k: None, 4, 64, 3, torch.float32, "cpu")
+    with pytest.raises(ValueError, match="depth"):
+        irr.SearchPipeline(lambda q, k: None, 4, 64, 3, torch.float32, "cuda", depth=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        irr.Gallery(torch.randn(8, 64))
+    with pytest.raises(ValueError):
+        irr.shard_bounds(-1, 2, 0)
