@@ -174,3 +174,59 @@ def test_get_fm_and_loss_ce_match_reference(golden_pc):
     (1.7 * tot).backward()
     assert torch.allclose(a.grad, T(g["ce_da"]), rtol=1e-6, atol=1e-9)
     assert torch.allclose(b.grad, T(g["ce_db"]), rtol=1e-6, atol=1e-9)
+
+
+# -------------------------------------------------------------------------------------------------
+# the independent closed-form restatement (numpy float64, no torch) against the same golden vectors
+# -------------------------------------------------------------------------------------------------
+from oracle import closed_forms as cf
+
+
+@pytest.mark.parametrize("tag", ["unit", "scaled"])
+@pytest.mark.parametrize("margin", MARGINS)
+def test_closed_forms_match_reference_losses_and_grads(golden_losses, tag, margin):
+    g = golden_losses
+    q, p, n = g[f"{tag}_q"], g[f"{tag}_p"], g[f"{tag}_n"]
+    losses, dq, dp, dn = cf.four_losses_and_grads(q, p, n, margin)
+    key = f"{tag}_m{margin}"
+    assert np.allclose(losses, g[key + "_losses"], rtol=2e-6, atol=1e-8)
+    for got, name in ((dq, "_dq"), (dp, "_dp"), (dn, "_dn")):
+        want = g[key + name].astype(np.float64)
+        assert np.linalg.norm(got - want) <= 2e-6 * np.linalg.norm(want), name
+    assert np.allclose(cf.pair_cos(q, p), g[f"{tag}_cos_sims"], atol=1e-6)
+    assert np.allclose(cf.pair_cos(q, n), g[f"{tag}_cos_unsims"], atol=1e-6)
+    sums = g[key + "_con_sum"]
+    assert np.isclose(cf.contrastive(q, p, 1.0, margin, mean=False)[0], sums[0], rtol=1e-6)
+    assert np.isclose(cf.contrastive(q, n, 0.0, margin, mean=False)[0], sums[1], rtol=1e-6)
+
+
+def test_closed_forms_match_reference_retrieval(golden_retrieval):
+    g = golden_retrieval
+    s = cf.cos_scores(g["planted_q"], g["planted_g"])
+    v, i = cf.topk_stable(s, 3)
+    assert np.array_equal(i, g["planted_inds"]) and np.array_equal(i, g["planted_pos"])
+    assert np.allclose(v, g["planted_vals"], rtol=1e-5)
+    v10, _ = cf.topk_stable(cf.cos_scores(g["iid_q"], g["iid_g"]), 10)
+    assert np.allclose(v10, g["iid_vals10"], rtol=1e-5, atol=1e-7)
+    vb, _ = cf.topk_stable(cf.cos_scores(g["batch_q"], g["batch_p"]), 3)
+    assert np.allclose(vb, g["batch_vals"], rtol=1e-5)
+
+
+def test_closed_forms_agree_with_the_torch_oracle_on_edge_cases():
+    q, gal = synthetic.tied_gallery(300, 32, 10, seed=3)
+    gal[5] = 0
+    q[2] = 0
+    gal[7] = gal[7] * 1e-9                      # below eps: clamped, not normalised
+    s = cf.cos_scores(q.numpy(), gal.numpy())
+    _, want_i, want_s = ref.cos_topk_stable(q, gal, 4)
+    assert np.allclose(s, want_s.double().numpy(), atol=2e-6)
+    # exact duplicate rows tie in float64 as well: lower index first, like the torch oracle
+    assert np.array_equal(cf.topk_stable(s, 2)[1][:, 0] < cf.topk_stable(s, 2)[1][:, 1],
+                          np.ones(10, dtype=bool))
+    vals = torch.randn(4, 9, 3).sort(dim=2, descending=True).values
+    idx = torch.stack([torch.randperm(100)[:3].sort().values + 100 * gg for gg in range(4) for _ in range(9)]).view(4, 9, 3)
+    vals[0, :, 0] = vals[1, :, 0]
+    idx[3, ::2, 2] = -1
+    mv, mi = cf.merge_candidates(vals.numpy(), idx.numpy(), 3)
+    wv, wi = ref.merge_candidates(vals, idx, 3)
+    assert np.array_equal(mi, wi.numpy()) and np.allclose(mv, wv.double().numpy())
