@@ -10,6 +10,11 @@ if str(ROOT) not in sys.path:
 
 GOLDEN = ROOT / "tests" / "golden"
 
+# the peer-exchange kernels wait for remote pushes with a watchdog (default: as patient as a
+# collective library); in the test process a protocol bug must trap within seconds, never hang.
+# The library reads the variable once, at its first exchange call.
+os.environ.setdefault("IRR_EXCHANGE_TIMEOUT_MS", "5000")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 with -m gpu)")
