@@ -37,6 +37,9 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
+# a rank that dies must not leave the others spinning for the library's default ten minutes
+os.environ.setdefault("IRR_EXCHANGE_TIMEOUT_MS", "60000")
+
 METRIC = "top-k cosine queries/s at 1Mx1536 gallery"
 UNIT = "queries/s"
 
