@@ -129,3 +129,18 @@ def test_paced_producers_and_waiting_consumers_always_finish(Q, N, ahead):
         assert all(cpos[c] == len(cons[c]) for c in range(2 * C)), "consumers stuck"
         assert all(ppos[n] == len(prods[n]) for n in range(NW)), "producers stuck"
         assert done == need
+
+
+@pytest.mark.parametrize("Q,N", SHAPES)
+def test_workspace_covers_the_pair_plan_and_the_tile_counters(Q, N):
+    """irr_cosine_topk_workspace_bytes (callable without a device) is at least what the pair
+    kernel's plan needs: cached norms + two partial-list arrays + row floors + per-tile counters."""
+    from imageretrievalresearch_b200 import _lib
+    lib = _lib.load()
+    m_pairs, n_tiles, tpc, n_chunks, _ = plan_pair(Q, N)
+    for k in (1, 3, 10, 16):
+        parts = n_chunks * Q * k
+        need = N * 4 + 2 * parts * 4 + Q * 4 + n_tiles * 4
+        got = lib.irr_cosine_topk_workspace_bytes(Q, N, 1536, k, _lib.IRR_BF16)
+        assert got >= need, (Q, N, k, got, need)
+        assert got <= need + 8 * 256 + max(need // 4, 1 << 16), "workspace far larger than the plan"
