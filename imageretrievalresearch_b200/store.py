@@ -6,7 +6,7 @@ returns them in a dict (inference/inference.py:245, 'normalized_embeddings').  T
 that gallery a form that survives the process and scales past one GPU's memory:
 
 * ``GalleryWriter`` / ``write_gallery`` — append ``get_fm`` outputs batch by batch into ONE file:
-  a 4 KiB header, then row-major ``[rows, D]`` embeddings (fp32 or bf16, exactly the layout the
+  a 4 KiB header, then row-major ``[rows, D]`` embeddings (fp32, bf16 or fp16, exactly the layout the
   kernels' TMA descriptors read — no transpose, no padding), then optional int64 labels and the
   fp32 inverse row norms ``1/max(|g|, eps)`` the search kernels consume.
 * ``GalleryStore`` — memory-maps the file; ``load`` a row range to a resident :class:`Gallery`,
@@ -41,8 +41,10 @@ HEADER_BYTES = 4096
 ALIGN = 4096
 # magic, version, dtype code, rows, dim, eps, emb_off, label_off, norm_off, file_bytes
 _HEADER = struct.Struct("<8sIIQIfQQQQ")
-_DTYPES = {0: (torch.float32, np.dtype("<f4"), 4), 1: (torch.bfloat16, np.dtype("<u2"), 2)}
-_CODES = {torch.float32: 0, torch.bfloat16: 1}
+# codes = irr_dtype (include/irr_b200.h); fp16 = the embeddings precision=16 training produces
+_DTYPES = {0: (torch.float32, np.dtype("<f4"), 4), 1: (torch.bfloat16, np.dtype("<u2"), 2),
+           2: (torch.float16, np.dtype("<f2"), 2)}
+_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 
 def _align(n: int) -> int:
@@ -76,7 +78,7 @@ class GalleryWriter:
     def __init__(self, path: Union[str, os.PathLike], dim: int, dtype: torch.dtype = torch.bfloat16,
                  eps: float = 1e-6, with_labels: bool = False) -> None:
         if dtype not in _CODES:
-            raise TypeError(f"unsupported gallery dtype {dtype} (fp32 or bf16)")
+            raise TypeError(f"unsupported gallery dtype {dtype} (fp32, bf16 or fp16)")
         if dim < 1 or (dim * _DTYPES[_CODES[dtype]][2]) % 16 != 0:
             raise ValueError(f"D={dim}: rows must be a multiple of 16 bytes (irr_b200.h alignment contract)")
         self.path = os.fspath(path)
@@ -96,10 +98,7 @@ class GalleryWriter:
             raise ValueError(f"expected [rows, {self.dim}] embeddings, got {tuple(embeddings.shape)}")
         if self.with_labels != (labels is not None):
             raise ValueError("labels must be given for every batch or for none")
-        e = embeddings.detach()
-        if e.dtype == torch.float16:
-            e = e.float()                      # autocast embeddings: widened like the search path does
-        e = e.to(self.dtype)
+        e = embeddings.detach().to(self.dtype)
         if e.is_cuda:
             self._norms.append(_ops.row_inv_norms(e, self.eps).cpu().numpy())
         else:
@@ -153,7 +152,7 @@ class GalleryBuilder:
     def __init__(self, dim: int, dtype: torch.dtype = torch.bfloat16, device="cuda",
                  capacity: int = 1 << 16, eps: float = 1e-6) -> None:
         if dtype not in _CODES:
-            raise TypeError(f"unsupported gallery dtype {dtype} (fp32 or bf16)")
+            raise TypeError(f"unsupported gallery dtype {dtype} (fp32, bf16 or fp16)")
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("GalleryBuilder lives on a CUDA device (there is no CPU fallback)")
@@ -209,7 +208,7 @@ def write_gallery(path: Union[str, os.PathLike], embeddings: torch.Tensor,
                   labels: Optional[torch.Tensor] = None, eps: float = 1e-6,
                   chunk_rows: int = 1 << 16) -> None:
     """Write a whole ``[rows, D]`` tensor (CPU or CUDA, fp32 / bf16) as one gallery file."""
-    dt = torch.float32 if embeddings.dtype in (torch.float32, torch.float16, torch.float64) else embeddings.dtype
+    dt = torch.float32 if embeddings.dtype == torch.float64 else embeddings.dtype
     with GalleryWriter(path, embeddings.shape[1], dt, eps, labels is not None) as w:
         for lo, hi in block_ranges(embeddings.shape[0], chunk_rows):
             w.append(embeddings[lo:hi], None if labels is None else labels[lo:hi])

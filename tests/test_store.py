@@ -16,7 +16,7 @@ from oracle import synthetic
 
 
 # ------------------------------------------------------------------------------------ CPU: format
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_file_roundtrip_and_layout(tmp_path, dtype):
     N, D = 1000, 72 if dtype == torch.float32 else 64
     emb = torch.randn(N, D).to(dtype)
@@ -96,7 +96,8 @@ def test_gather_embeddings_gloo_world2():
 
 # ------------------------------------------------------------------------------------ GPU: parity
 @pytest.mark.gpu
-@pytest.mark.parametrize("dtype,k", [(torch.bfloat16, 3), (torch.float32, 3), (torch.bfloat16, 150)])
+@pytest.mark.parametrize("dtype,k", [(torch.bfloat16, 3), (torch.float32, 3), (torch.bfloat16, 150),
+                                     (torch.float16, 3)])
 @pytest.mark.parametrize("pinned", [True, False])
 def test_streamed_equals_resident(dtype, k, pinned):
     N, D, Q = 50_011, 256, 70
