@@ -12,6 +12,14 @@ peer over NVLink peer memory, flags, waits and merges (csrc/topk_exchange.cu); i
 cannot be mapped the ranks agree on an NCCL all-gather + merge kernel instead (`config.exchange`
 says which ran).
 
+After the timed regions the line is VERIFIED: the merged top-k of 16 sampled queries from a plain
+search is compared with a chunked torch fp32 scan of every rank's shard (all-gathered and merged in
+torch) — `"verified": true`, or the process exits non-zero.  The line also carries the other
+configurations BASELINE.json names (`sweep`: Q=1 / Q=64 as fractions of the HBM roofline; `losses`:
+the fused loss kernel at 4096 x 1536 fp32 and bf16; `fp32_10k`: configs[1]) and `torch_gpu_baseline`:
+torch's own CUDA path on the same GPU (batched bf16 cuBLAS + torch.topk, and the reference's literal
+per-query loop).
+
 A step = one search of all Q queries: the tcgen05 top-k kernel — whose four norm-producer warps
 per CTA recompute the inverse row norms of the gallery shard inside the same launch, every step:
 nothing is cached across steps — the partial-list merge, and for
@@ -55,7 +63,8 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=1536)
     ap.add_argument("--k", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also time Q=1 and Q=64 (extra keys)")
+    ap.add_argument("--no-sweep", action="store_true",
+                    help="skip the extra keys (Q=1/64, losses, fp32_10k, torch_gpu_baseline)")
     return ap.parse_args()
 
 
@@ -69,9 +78,13 @@ def measured_peaks():
             "source": "fallback"}
 
 
-def workload_name(a, world):
+def workload_name(a, world, transport=None):
+    how = ""
+    if world > 1:
+        how = {"peer": " + peer-memory exchange/merge kernel over NVLink",
+               "collective": " + NCCL all-gather and merge kernel"}.get(transport, " + candidate exchange and merge")
     return (f"cosine top-{a.k} over a {a.rows}x{a.dim} bf16 gallery, Q={a.queries} per step, "
-            f"gallery row-sharded over {world} GPU(s)" + (" + NCCL all-gather merge" if world > 1 else ""))
+            f"gallery row-sharded over {world} GPU(s)" + how)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -212,6 +225,180 @@ def cpu_baseline(a, gallery_dev):
 # -------------------------------------------------------------------------------------------------
 # this repo's arm
 # -------------------------------------------------------------------------------------------------
+def graphed_us(fn, calls, replays=5):
+    """`calls` invocations of fn(i) captured into one CUDA graph; microseconds per invocation on the
+    device (the python wrapper costs more host time than the small kernels take)."""
+    import torch
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        for i in range(calls):
+            fn(i)
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for i in range(calls):
+                fn(i)
+        for _ in range(3):
+            g.replay()
+        st.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(st)
+        for _ in range(replays):
+            g.replay()
+        e.record(st)
+        st.synchronize()
+    return s.elapsed_time(e) / (replays * calls) * 1e3
+
+
+def event_ms(fn, iters, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def verify_against_torch(irr, dist, search_plain, queries, shard, lo, N, k, world, dev, n_check=16):
+    """Outside the timed regions: the merged top-k of `n_check` sampled queries against a chunked
+    torch fp32 scan of this rank's shard, all-gathered over the ranks and merged in torch
+    (normalize + matmul + topk: torch's own restatement of the reference's cos + topk,
+    train/train_efficient_cos_con_ce_loss.py:273-276).  Indices must be identical except where the
+    torch score gap is below 1e-4 (the kernels are within ~3e-6 of fp64 on bf16 inputs; iid
+    galleries have near-ties); values within the bf16-mode bar of 2e-2 absolute."""
+    import torch
+    import torch.nn.functional as F
+    Q = queries.shape[0]
+    sel = torch.linspace(0, Q - 1, steps=min(n_check, Q), device=dev).long()
+    res = search_plain(queries)
+    got_v, got_i = res.values[sel], res.indices[sel]
+    qs = F.normalize(queries[sel].float(), dim=1, eps=1e-6)
+    kk = min(k + 2, max(shard.shape[0], 1))
+    best_v = torch.full((len(sel), kk), -float("inf"), device=dev)
+    best_i = torch.full((len(sel), kk), -1, dtype=torch.int64, device=dev)
+    for b0 in range(0, shard.shape[0], 131072):
+        blk = F.normalize(shard[b0:b0 + 131072].float(), dim=1, eps=1e-6)
+        v, i = torch.topk(qs @ blk.T, min(kk, blk.shape[0]), dim=1)
+        allv, alli = torch.cat([best_v, v], 1), torch.cat([best_i, i + lo + b0], 1)
+        o = torch.argsort(allv, dim=1, descending=True, stable=True)[:, :kk]
+        best_v, best_i = allv.gather(1, o), alli.gather(1, o)
+    if world > 1:
+        gv = [torch.empty_like(best_v) for _ in range(world)]
+        gi = [torch.empty_like(best_i) for _ in range(world)]
+        dist.all_gather(gv, best_v)
+        dist.all_gather(gi, best_i)
+        allv, alli = torch.cat(gv, 1), torch.cat(gi, 1)
+        o = torch.argsort(allv, dim=1, descending=True, stable=True)[:, :kk]
+        best_v, best_i = allv.gather(1, o), alli.gather(1, o)
+    want_v, want_i = best_v[:, :k], best_i[:, :k]
+    val_err = (got_v - want_v).abs().max().item()
+    same = got_i == want_i
+    # a differing index is fine only where torch's own candidates are within 1e-4 of each other
+    near = torch.zeros_like(same)
+    for j in range(k):
+        hit = (best_i == got_i[:, j:j + 1])
+        picked = torch.where(hit, best_v, torch.full_like(best_v, -float("inf"))).max(dim=1).values
+        near[:, j] = (picked - want_v[:, j]).abs() < 1e-4
+    bad = int((~same & ~near).sum().item())
+    ok = bad == 0 and val_err < 2e-2
+    if world > 1:
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+    return {"verified": ok, "queries_checked": int(len(sel)), "max_abs_score_err": val_err,
+            "indices_identical_frac": same.float().mean().item(), "bad_indices": bad,
+            "against": "chunked torch fp32 normalize+matmul+topk over every rank's shard, merged in torch"}
+
+
+def torch_gpu_baseline(a, queries, shard, ours_ms):
+    """torch's own CUDA path on the same GPU: (1) the batched restatement in bf16 — normalise, cuBLAS
+    GEMM per gallery chunk, torch.topk, running merge — with the gallery normalised every step like
+    the timed search does; (2) the reference's literal per-query loop
+    (inference/training_analysis.ipynb:238, train_efficient_cos_con_ce_loss.py:273-276) on fp32
+    embeddings for 16 sampled queries."""
+    import torch
+    import torch.nn.functional as F
+    Q, k = queries.shape[0], a.k
+    chunk = 65536
+
+    def batched():
+        qn = F.normalize(queries.float(), dim=1, eps=1e-6).bfloat16()
+        bv = bi = None
+        for b0 in range(0, shard.shape[0], chunk):
+            gn = F.normalize(shard[b0:b0 + chunk].float(), dim=1, eps=1e-6).bfloat16()
+            v, i = torch.topk(qn @ gn.T, k, dim=1)
+            i = i + b0
+            if bv is None:
+                bv, bi = v, i
+            else:
+                allv, alli = torch.cat([bv, v], 1), torch.cat([bi, i], 1)
+                o = torch.topk(allv, k, dim=1).indices
+                bv, bi = allv.gather(1, o), alli.gather(1, o)
+        return bv, bi
+
+    ms_b = event_ms(batched, 3, warm=1)
+    g32 = shard.float()
+    cos = torch.nn.CosineSimilarity(dim=1, eps=1e-6)
+    q32 = queries[:16].float()
+
+    def loop():
+        for j in range(q32.shape[0]):
+            torch.topk(cos(q32[j].unsqueeze(0), g32), k)
+
+    ms_l = event_ms(loop, 2, warm=1) / q32.shape[0]
+    del g32
+    torch.cuda.empty_cache()
+    return {"batched_bf16_cublas_topk": {"ms_per_step": ms_b, "queries_per_s": Q / (ms_b * 1e-3),
+                                         "what": f"normalize + bf16 matmul + torch.topk per {chunk}-row chunk, gallery normalised every step"},
+            "reference_loop_same_gpu": {"ms_per_query": ms_l, "queries_per_s": 1e3 / ms_l,
+                                        "what": "per-query CosineSimilarity(dim=1,eps=1e-6)+torch.topk on fp32 embeddings, 16 sampled queries"},
+            "x_over_torch_cuda_batched": ms_b / ours_ms,
+            "x_over_reference_loop_same_gpu": (ms_l * Q) / ours_ms}
+
+
+def extra_configs(irr, a, queries, shard, peaks, search):
+    """The other configurations BASELINE.json names, each a few milliseconds of GPU time."""
+    import torch
+    D, k, n_local = a.dim, a.k, shard.shape[0]
+    out = {}
+    sweep = []
+    for qs in (1, 64):
+        qq = queries[:qs].contiguous()
+        ms = event_ms(lambda: search(qq), a.steps)
+        b = n_local * D * 2 + qs * D * 2 + qs * k * 12
+        sweep.append({"Q": qs, "ms_per_step": ms, "queries_per_s": qs / (ms * 1e-3),
+                      "hbm_frac_of_step": b / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "algorithmic_bytes": b})
+    out["sweep"] = sweep
+    # configs[2]: fused contrastive + cosine-embedding losses fwd+bwd, 4096 x 1536 triplets.
+    # 151 MB (fp32) per call is about the size of L2: rotate over 6 input sets (> 2x L2).
+    B, LD = 4096, 1536
+    losses = []
+    for dt in (torch.float32, torch.bfloat16):
+        sets = [[torch.randn(B, LD, device=queries.device).to(dt) for _ in range(3)] for _ in range(6)]
+        us = graphed_us(lambda i: irr.triplet_losses_fwd_bwd(*sets[i % 6], 0.3), 24)
+        by = 6 * B * LD * sets[0][0].element_size()
+        losses.append({"dtype": str(dt).replace("torch.", ""), "B": B, "D": LD, "us": us,
+                       "algorithmic_bytes": by, "GBps": by / us / 1e3,
+                       "hbm_frac": by / us / 1e3 / peaks["hbm_gbs"], "triplets_per_s": B / (us * 1e-6),
+                       "timing": "CUDA graph of 24 launches over 6 rotating input sets"})
+        del sets
+    out["losses"] = losses
+    # configs[1]: fp32 exactness path, 10k x 1536, Q=64, k=3 (gallery fits L2: report time)
+    g32 = torch.randn(10_000, 1536, device=queries.device)
+    q32 = torch.randn(64, 1536, device=queries.device)
+    us = graphed_us(lambda i: irr.cosine_topk(q32, g32, 3), 10)
+    out["fp32_10k"] = {"Q": 64, "N": 10_000, "D": 1536, "k": 3, "us": us, "queries_per_s": 64 / (us * 1e-6),
+                       "timing": "CUDA graph of 10 searches"}
+    return out
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -234,6 +421,7 @@ def run_b200(a):
     shard = torch.randn(hi - lo, D, device=dev, dtype=torch.bfloat16, generator=gen)
     qgen = torch.Generator(device=dev).manual_seed(11)
     queries = torch.randn(Q, D, device=dev, dtype=torch.bfloat16, generator=qgen)
+    gallery = None
     if world > 1:
         gallery = irr.ShardedGallery(shard, N, cache_norms=False)
         search = lambda q: gallery.search(q, k)
@@ -255,42 +443,48 @@ def run_b200(a):
     # ---- device-resident timing (value) with per-launch timing of the dominant kernel ----
     for _ in range(a.warmup):
         search(queries)
+    transport = gallery.transport if gallery is not None else None
     # N > 1 with the peer-memory exchange: the stream of searches runs lagged (each search's
     # rendezvous is with the peers' PREVIOUS push, ShardedGallery.search_lagged), so a step does
     # not cost the slowest of N kernels; every search's merged result is still produced inside the
-    # timed region (the last one by flush()).  IRR_BENCH_LAGGED=0 times the plain search instead.
-    lagged = (world > 1 and gallery.transport == "peer" and k <= 16
-              and os.environ.get("IRR_BENCH_LAGGED", "1") != "0")
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(a.steps)]
-    for s, e in kev:            # force creation of the raw cudaEvent_t handles
-        s.record(); e.record()
+    # timed region (the last one by flush()).  `value_plain` times the plain search (every step
+    # ends in a rendezvous) in a second region; IRR_BENCH_LAGGED=0 makes that one the headline.
+    can_lag = world > 1 and transport == "peer" and k <= 16
+    lagged = can_lag and os.environ.get("IRR_BENCH_LAGGED", "1") != "0"
+    prof_every = int(os.environ.get("IRR_BENCH_PROF_EVERY", "1"))
     # NVML is initialised and the sampler thread is running BEFORE the ranks line up: anything a
     # rank does between the barrier and its first launch is waited for by every other rank in the
     # first exchange and would be charged to all of their timers
     sampler = ClockSampler(local, enabled=(rank == 0))
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record(); stop.record()          # create the raw handles ahead of the barrier, too
-    with sampler as clocks:
+
+    def timed_region(use_lagged, profile):
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(a.steps)]
+        for s, e in kev:            # force creation of the raw cudaEvent_t handles
+            s.record(); e.record()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(); stop.record()          # create the raw handles ahead of the barrier, too
         barrier()
         start.record()
-        prof_every = int(os.environ.get("IRR_BENCH_PROF_EVERY", "1"))
         for j, (s, e) in enumerate(kev):
-            if prof_every > 0 and j % prof_every == 0:
+            if profile and prof_every > 0 and j % prof_every == 0:
                 lib.irr_profile_next_topk(s.cuda_event, e.cuda_event)
-            if lagged:
+            if use_lagged:
                 gallery.search_lagged(queries, k)
             else:
                 search(queries)
-        if lagged:
+        if use_lagged:
             gallery.flush()
         stop.record()
         barrier()
-    ms_total = max_over_ranks(start.elapsed_time(stop))
-    ms_step = ms_total / a.steps
-    timed = [(s, e) for j, (s, e) in enumerate(kev) if prof_every > 0 and j % prof_every == 0]
-    kernel_ms = sum(s.elapsed_time(e) for s, e in timed) / len(timed) if timed else ms_step
-    kernel_ms = max_over_ranks(kernel_ms)
+        ms_step = max_over_ranks(start.elapsed_time(stop)) / a.steps
+        timed = [(s, e) for j, (s, e) in enumerate(kev) if profile and prof_every > 0 and j % prof_every == 0]
+        kernel_ms = sum(s.elapsed_time(e) for s, e in timed) / len(timed) if timed else ms_step
+        return ms_step, max_over_ranks(kernel_ms)
+
+    with sampler as clocks:
+        ms_step, kernel_ms = timed_region(lagged, True)
+        ms_other = timed_region(not lagged, False)[0] if can_lag else None
     value = Q / (ms_step * 1e-3)
 
     # ---- end to end through the public API with host buffers (e2e) ----
@@ -318,7 +512,10 @@ def run_b200(a):
            "d2h_bytes_per_step": pipe.d2h_bytes_per_batch,
            "api": "SearchPipeline.run over pinned host batches (copy / search / read-back overlapped)"}
 
-    # ---- roofline of the dominant kernel (cosine_topk_bf16_kernel) ----
+    # ---- the result itself, outside the timed regions, at every N ----
+    verified = verify_against_torch(irr, dist, search, queries, shard, lo, N, k, world, dev)
+
+    # ---- roofline of the dominant kernel ----
     peaks = measured_peaks()
     n_local = hi - lo
     flops = 2.0 * Q * n_local * D
@@ -339,30 +536,15 @@ def run_b200(a):
         ach = bytes_alg / (kernel_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic}
-    kname = "cosine_topk_bf16_pair_kernel" if Q > 384 else "cosine_topk_bf16_kernel"
+    kname = "cosine_topk_bf16_pair_kernel" if Q > 128 else "cosine_topk_bf16_kernel"
     roof.update({"kernel": kname, "kernel_ms": kernel_ms, "peak_source": peaks["source"],
                  "kernel_share_of_step": kernel_ms / ms_step,
                  "algorithmic": {"flops": flops, "bytes": bytes_alg}})
 
     extra = {}
-    if a.sweep and world == 1:
-        sweep = []
-        for qs in (1, 64):
-            qq = queries[:qs].contiguous()
-            for _ in range(3):
-                search(qq)
-            torch.cuda.synchronize()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(a.steps):
-                search(qq)
-            s1.record()
-            torch.cuda.synchronize()
-            ms = s0.elapsed_time(s1) / a.steps
-            b = n_local * D * 2 + qs * D * 2 + qs * k * 12
-            sweep.append({"Q": qs, "ms_per_step": ms, "queries_per_s": qs / (ms * 1e-3),
-                          "hbm_frac_of_step": b / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]})
-        extra["sweep"] = sweep
+    if not a.no_sweep and world == 1:
+        extra = extra_configs(irr, a, queries, shard, peaks, search)
+        extra["torch_gpu_baseline"] = torch_gpu_baseline(a, queries, shard, ms_step)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -371,29 +553,36 @@ def run_b200(a):
         dist.barrier()
 
     if rank == 0:
-        # top-k (gallery norms produced inside it), partial merge (+ the fused exchange/merge kernel, or
-        # the lagged pair merge-of-previous + push); 257..512 queries
-        # without cached norms still run the streaming norm pre-pass kernel
-        launches_per_step = 2 + (1 if 256 < Q <= 512 else 0) + ((2 if lagged else 1) if world > 1 else 0)
+        # kernels per step: the top-k kernel (gallery norms produced inside it) and the partial-list
+        # merge, + for N > 1 the fused exchange/merge kernel (lagged: merge-of-previous + push)
+        launches_per_step = 2 + ((2 if lagged else 1) if world > 1 else 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(a, world), "Q": Q, "N": N, "D": D, "k": k,
+            "config": {"workload": workload_name(a, world, transport), "Q": Q, "N": N, "D": D, "k": k,
                        "parallelism": f"gallery rows sharded x{world}",
                        "l2": "inputs larger than L2 (gallery shard streamed every step); no flush",
                        "norms": "inverse gallery norms recomputed every step inside the top-k kernel (no cached state)",
                        "exchange": (("peer-memory exchange+merge kernel (" + gallery._peer.mapping + ")"
                                      + (", lagged by one search in the value loop" if lagged else ""))
-                                    if world > 1 and gallery.transport == "peer" else
+                                    if world > 1 and transport == "peer" else
                                     ("nccl all-gather + merge kernel" if world > 1 else "none"))},
             "e2e": e2e, "gpu_launches": launches_per_step * a.steps, "clocks": clocks.summary(),
             "roofline": roof, "cpu_baseline": cpu,
         }
+        line.update(verified)
+        if can_lag:
+            ms_l, ms_p = (ms_step, ms_other) if lagged else (ms_other, ms_step)
+            line["value_lagged"] = Q / (ms_l * 1e-3)
+            line["value_plain"] = Q / (ms_p * 1e-3)
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not verified["verified"]:
+        print(f"bench.py: rank {rank}: result verification FAILED: {verified}", file=sys.stderr, flush=True)
+        sys.exit(3)
 
 
 def main():

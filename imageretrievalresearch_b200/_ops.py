@@ -80,12 +80,18 @@ def scratch(device: torch.device, nbytes: int) -> torch.Tensor:
 
 
 def zeroed_scratch(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Workspace that is zero-filled once (self-resetting sync words, see irr_b200.h)."""
+    """Workspace that is zero-filled once (self-resetting sync words, see irr_b200.h).  While a
+    CUDA graph is being captured the buffer (and its zero-fill, recorded as a graph node) comes
+    from the graph's own memory pool and is never cached: memory of that pool is recycled once the
+    capture ends, so a cached sync word could be non-zero — or somebody else's tensor — later."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _zeroed.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
-        _zeroed[key] = buf
+    if buf is not None and buf.numel() >= nbytes:
+        return buf            # allocated eagerly (ordinary pool, kept alive here): fine inside a capture too
+    if torch.cuda.is_current_stream_capturing():
+        return torch.zeros(max(nbytes, 256), dtype=torch.uint8, device=device)
+    buf = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+    _zeroed[key] = buf
     return buf
 
 

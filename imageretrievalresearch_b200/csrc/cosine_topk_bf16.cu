@@ -23,6 +23,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "irr_common.cuh"
 #include "irr_kernels.h"
 
@@ -50,11 +52,37 @@ struct Plan {
   int m_tiles, n_tiles, tiles_per_chunk, n_chunks, grid;
 };
 
+// Measurement knobs for profiles/ (environment, read ONCE per process) — not an API.
+struct Knobs {
+  int tiles_per_chunk;       // IRR_TILES_PER_CHUNK: override the planner's chunk length
+  bool no_pair, force_pair;  // IRR_NO_PAIR=1 / IRR_FORCE_PAIR=1: kernel choice
+  bool producers;            // IRR_NORMS_INSIDE=0: no in-kernel norm producers
+  int producers_min_pairs;   // IRR_NORMS_MIN_PAIRS: query-tile pairs from which the producers are used
+  int norm_ahead;            // IRR_NORM_AHEAD: tiles the producers may run ahead (negative = unpaced)
+  bool fused_pair;           // IRR_FUSED_PAIR=0: no fused norms in the pair kernel (pre-pass instead)
+};
+const Knobs& knobs() {
+  static const Knobs k = []() {
+    auto num = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    auto flag = [](const char* name, char c) { const char* e = getenv(name); return e && e[0] == c; };
+    Knobs r;
+    r.tiles_per_chunk = num("IRR_TILES_PER_CHUNK", 0);
+    r.no_pair = flag("IRR_NO_PAIR", '1');
+    r.force_pair = flag("IRR_FORCE_PAIR", '1');
+    r.producers = !flag("IRR_NORMS_INSIDE", '0');
+    r.producers_min_pairs = num("IRR_NORMS_MIN_PAIRS", 3);
+    r.norm_ahead = num("IRR_NORM_AHEAD", 2);
+    r.fused_pair = !flag("IRR_FUSED_PAIR", '0');
+    return r;
+  }();
+  return k;
+}
+
 // Chunk the gallery tiles so that (query tiles x chunks) spreads evenly over the SMs.
-Plan make_plan(int64_t Q, int64_t N, int MT = 1) {
+Plan make_plan(int64_t Q, int64_t N) {
   Plan p;
   const int sms = num_sms();
-  p.m_tiles = static_cast<int>((Q + MT * BLOCK_M - 1) / (MT * BLOCK_M));
+  p.m_tiles = static_cast<int>((Q + BLOCK_M - 1) / BLOCK_M);
   p.n_tiles = static_cast<int>((N + BLOCK_N - 1) / BLOCK_N);
   if (p.m_tiles < 1) p.m_tiles = 1;
   if (p.n_tiles < 1) p.n_tiles = 1;
@@ -73,10 +101,8 @@ Plan make_plan(int64_t Q, int64_t N, int MT = 1) {
       best_tpc = tpc;
     }
   }
-  if (const char* e = getenv("IRR_TILES_PER_CHUNK")) {  // measurement knob (profiles/), not an API
-    const int v = atoi(e);
-    if (v >= 1 && v <= p.n_tiles) best_tpc = v;
-  }
+  const int forced = knobs().tiles_per_chunk;
+  if (forced >= 1 && forced <= p.n_tiles) best_tpc = forced;
   p.tiles_per_chunk = best_tpc;
   p.n_chunks = (p.n_tiles + best_tpc - 1) / best_tpc;
   const long long units = 1ll * p.n_chunks * p.m_tiles;
@@ -223,33 +249,26 @@ __device__ __forceinline__ void publish_floor(uint32_t* row_floor, int row, int 
   if (row < Q && top.v[KMAX - 1] > floor) atomicMax(row_floor + row, orderable(top.v[KMAX - 1]));
 }
 
-// Geometry of the single-CTA kernel for MT query tiles (MT*128 rows) per work unit.
-//   MT = 1: 4 stages x (16 KB A + 32 KB B), two accumulator stages (2 x 256 TMEM columns)
-//   MT = 2: 3 stages x (32 KB A + 32 KB B), ONE accumulator stage holding both tiles (2 x 256
-//           columns): a gallery tile is staged once and multiplied against 256 query rows, so
-//           batches of 129..512 queries stream the gallery once per 256 queries instead of once per
-//           128.  That regime is HBM-bound, so the epilogue not overlapping the next tile's MMAs
-//           costs little (the TMA ring keeps filling meanwhile).
-template <int MT>
+// Geometry of the single-CTA kernel: 4 stages x (16 KB A + 32 KB B), two accumulator stages
+// (2 x 256 TMEM columns).
 struct SC {
-  static constexpr int STAGES = MT == 1 ? 4 : 3;
-  static constexpr int ACC = MT == 1 ? 2 : 1;
-  static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int A_BYTES = MT * A_TILE_BYTES;
+  static constexpr int STAGES = 4;
+  static constexpr int ACC = ACC_STAGES;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   static constexpr int TILES = STAGES * STAGE_BYTES;
   static constexpr int GN = ACC * BLOCK_N * 4;
   static constexpr int BARS = (2 * STAGES + 3 * ACC) * 8;
   static constexpr int ALLOC = TILES + GN + BARS + 16 + 1024;
-  static_assert(MT * ACC * BLOCK_N <= TMEM_COLS, "accumulators exceed TMEM");
+  static_assert(ACC * BLOCK_N <= TMEM_COLS, "accumulators exceed TMEM");
   static_assert(TILES <= 196608, "stage ring exceeds the shared-memory budget");
 };
 
 // FUSE_NORM: four extra warps square-sum the gallery rows out of the SAME shared-memory stages the
 // MMA reads, so the gallery crosses HBM once per search and no inverse-norm pre-pass exists (used
-// when a gallery tile has one or two consumers; with many query tiles the norms come from
+// when a gallery tile has a single consumer; with several query tiles the norms come from
 // g_inv_norm instead).
-template <int KMAX, bool WRITE_SCORES, bool FUSE_NORM, int MT>
+template <int KMAX, bool WRITE_SCORES, bool FUSE_NORM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         const __grid_constant__ CUtensorMap tmap_g,
@@ -259,7 +278,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         int32_t* __restrict__ part_idx, float* __restrict__ scores_out,
                         uint64_t g_policy, float eps, int a_rows, uint32_t* __restrict__ row_floor,
                         int is_f16) {
-  using G = SC<MT>;
+  using G = SC;
   constexpr int STAGES = G::STAGES;
   constexpr int ACC = G::ACC;
   constexpr int STAGE_BYTES = G::STAGE_BYTES;
@@ -300,9 +319,9 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
-  if (a_rows < MT * BLOCK_M) {
+  if (a_rows < BLOCK_M) {
     // small query batch: the TMA box only covers the first a_rows rows of each A stage; the MMA
-    // still reads MT*128 rows, so the rest is zeroed once here (their accumulator rows are ignored)
+    // still reads 128 rows, so the rest is zeroed once here (their accumulator rows are ignored)
     for (int s = 0; s < STAGES; ++s) {
       uint4* a = reinterpret_cast<uint4*>(smem_gen + s * STAGE_BYTES);
       for (int i = threadIdx.x; i < G::A_BYTES / 16; i += NUM_THREADS)
@@ -332,7 +351,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
             const uint32_t b_dst = a_dst + G::A_BYTES;
             mbar_arrive_expect_tx(full_bar(stage), a_rows * (BLOCK_K * 2) + B_STAGE_BYTES);
-            tma_load_2d(a_dst, &tmap_q, kb * BLOCK_K, mt * (MT * BLOCK_M), full_bar(stage),
+            tma_load_2d(a_dst, &tmap_q, kb * BLOCK_K, mt * BLOCK_M, full_bar(stage),
                         kPolicyEvictLast);
             tma_load_2d(b_dst, &tmap_g, kb * BLOCK_K, t * BLOCK_N, full_bar(stage), g_policy);
           }
@@ -355,22 +374,19 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t as = it % ACC, aphase = (it / ACC) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u, 200 + as);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + as * (MT * BLOCK_N);
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, 300 + stage);
           tcgen05_fence_after();
           if (lane == 0) {
             const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+            const uint64_t adesc = umma_desc_k128(a_addr);
             const uint64_t bdesc = umma_desc_k128(a_addr + G::A_BYTES);
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              const uint64_t adesc = umma_desc_k128(a_addr + m * G::A_TILE_BYTES);
-#pragma unroll
-              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-                // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-byte units
-                umma_bf16_ss(tmem_d + m * BLOCK_N, adesc + 2u * kk, bdesc + 2u * kk, idesc,
-                             (kb > 0 || kk > 0) ? 1u : 0u);
-              }
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+              // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-byte units
+              umma_bf16_ss(tmem_d, adesc + 2u * kk, bdesc + 2u * kk, idesc,
+                           (kb > 0 || kk > 0) ? 1u : 0u);
             }
             umma_commit(empty_bar(stage));                 // frees the smem stage when MMAs finish
             if (kb == num_kb - 1) umma_commit(tfull_bar(as));  // accumulator(s) ready
@@ -427,17 +443,16 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
     const int row_in_tile = ew * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
-    TopKList<KMAX, int32_t> top[MT];
+    TopKList<KMAX, int32_t> top;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int chunk = u / m_tiles, mt = u - chunk * m_tiles;
       const int t0 = chunk * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
-      const int row0 = mt * (MT * BLOCK_M) + row_in_tile;   // this thread's row in query tile 0
-#pragma unroll
-      for (int m = 0; m < MT; ++m) top[m].reset();
+      const int row = mt * BLOCK_M + row_in_tile;
+      top.reset();
       float qn = 1.0f;
-      if (WRITE_SCORES && row0 < Q) qn = q_inv_norm[row0];
+      if (WRITE_SCORES && row < Q) qn = q_inv_norm[row];
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t as = it % ACC, aphase = (it / ACC) & 1u;
         const int n0 = t * BLOCK_N;
@@ -453,31 +468,21 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_wait(tfull_bar(as), aphase, 400 + as);
         tcgen05_fence_after();
         const int n_valid = min(BLOCK_N, N - n0);
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const int row = row0 + m * BLOCK_M;
-          const float floor = WRITE_SCORES ? kNegInf : read_floor(row_floor, row, Q);
-          epilogue_tile<KMAX, WRITE_SCORES>(tmem_base + lane_base + (as * MT + m) * BLOCK_N, gn, n0,
-                                            n_valid, row, Q, N, qn, scores_out, top[m], floor);
-          if (!WRITE_SCORES) publish_floor<KMAX>(row_floor, row, Q, top[m], floor);
-        }
+        const float floor = WRITE_SCORES ? kNegInf : read_floor(row_floor, row, Q);
+        epilogue_tile<KMAX, WRITE_SCORES>(tmem_base + lane_base + as * BLOCK_N, gn, n0, n_valid, row,
+                                          Q, N, qn, scores_out, top, floor);
+        if (!WRITE_SCORES) publish_floor<KMAX>(row_floor, row, Q, top, floor);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
       }
-      if (!WRITE_SCORES) {
+      if (!WRITE_SCORES && row < Q) {
+        const size_t o = (static_cast<size_t>(chunk) * Q + row) * k;
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const int row = row0 + m * BLOCK_M;
-          if (row < Q) {
-            const size_t o = (static_cast<size_t>(chunk) * Q + row) * k;
-#pragma unroll
-            for (int j = 0; j < KMAX; ++j) {
-              if (j < k) {
-                part_val[o + j] = top[m].v[j];
-                part_idx[o + j] = top[m].i[j];
-              }
-            }
+        for (int j = 0; j < KMAX; ++j) {
+          if (j < k) {
+            part_val[o + j] = top.v[j];
+            part_idx[o + j] = top.i[j];
           }
         }
       }
@@ -511,12 +516,17 @@ constexpr int P_A_BYTES = BLOCK_M * BLOCK_K * 2;               // 16 KB
 constexpr int P_B_BYTES = P_B_ROWS * BLOCK_K * 2;              // 16 KB
 constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;           // 32 KB
 constexpr int P_SMEM_TILES = P_STAGES * P_STAGE_BYTES;         // 196608
-constexpr int P_SMEM_BARS = (2 * P_STAGES + 2 * ACC_STAGES) * 8;
+// full / empty / norm-done per stage, accumulator full / empty / norms-published per accumulator stage
+constexpr int P_SMEM_BARS = (3 * P_STAGES + 3 * ACC_STAGES) * 8;
 constexpr int P_SMEM_TOTAL = P_SMEM_TILES + SMEM_GN + P_SMEM_BARS + 16;
 constexpr int P_SMEM_ALLOC = P_SMEM_TOTAL + 1024;
 constexpr int P_THREADS = 256;
-constexpr int P_NORM_WARP0 = 8;            // NORMS_INSIDE: warps 8-11 produce the gallery norms
+constexpr int P_NORM_WARP0 = 8;            // warps 8-11 of the variants that make their own gallery norms
 constexpr int P_THREADS_NORM = 384;
+// where the pair kernel's inverse gallery norms come from
+constexpr int NORMS_CACHED = 0;      // g_inv_norm (the caller's Gallery cache)
+constexpr int NORMS_PRODUCERS = 1;   // grid-wide in-kernel producers reading global memory (>= 3 pairs)
+constexpr int NORMS_FUSED = 2;       // square-summed from the staged gallery tiles (1-2 pairs)
 constexpr int OCTET = 8;                   // rows a norm warp finishes between two publications
 constexpr int OCTETS_PER_TILE = BLOCK_N / OCTET;
 
@@ -611,18 +621,51 @@ __device__ __forceinline__ void norm_octet(const uint4* __restrict__ g_rows, int
   }
 }
 
-// NORMS_INSIDE (no cached norms): instead of a streaming pre-pass kernel, four extra warps per CTA
+// One square-summed 128-byte slice (64 elements) of ONE gallery row out of a staged tile, same
+// logical chunk order and accumulator split as norm_stage_sums (so every fused-norm variant gives a
+// row the same bits wherever it sits).
+template <bool F16>
+__device__ __forceinline__ void norm_row_sums(const uint4* r, int nt, float& sa, float& sb) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const uint4 u0 = r[j ^ (nt & 7)], u1 = r[(j + 1) ^ (nt & 7)];
+    const uint32_t x0[4] = {u0.x, u0.y, u0.z, u0.w}, x1[4] = {u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = unpack16x2(x0[e], F16);
+      sa = fmaf(f.x, f.x, sa); sa = fmaf(f.y, f.y, sa);
+      f = unpack16x2(x1[e], F16);
+      sb = fmaf(f.x, f.x, sb); sb = fmaf(f.y, f.y, sb);
+    }
+  }
+}
+
+// Where the inverse gallery norms of the pair kernel come from (template parameter NORMS):
+//
+// NORMS_FUSED (no cached norms, one or two query-tile pairs): L2-normalisation fused into the load.
+// Four extra warps per CTA square-sum the CTA's half of every gallery tile out of the SAME
+// shared-memory stages the MMAs read — after the stage's MMAs retired (they wait on the stage's
+// "empty" barrier, which tcgen05.commit multicasts to both CTAs) and before the TMA producer may
+// refill it (it also waits on the stage's "norm done" barrier) — and publish 1/max(|g|,eps) of
+// their 128 rows into BOTH CTAs' norm buffers (own shared memory + a DSMEM store to the partner),
+// arriving on both CTAs' "norms published" barrier.  The gallery crosses HBM once, nothing is
+// exchanged through global memory and no CTA waits for a CTA outside its own cluster.  With many
+// query-tile pairs every pair would recompute the norms of the tiles it streams (16x at Q=4096),
+// which is why three pairs and up use the producers below instead.
+//
+// NORMS_PRODUCERS (no cached norms, three or more pairs): instead of a streaming pre-pass kernel, four extra warps per CTA
 // compute 1/max(|g|,eps) for the WHOLE gallery cooperatively across the grid, straight from global
 // memory, in the order the tile stream will need the tiles (the chunks that start together are
 // interleaved tile by tile), publish each finished octet of rows on a per-tile counter (fence +
 // atomic), and are done after about the time the pre-pass used to take — but concurrently with the
 // MMAs, which leave most of the DRAM bandwidth idle.  The epilogue waits (acquire) for its tile's
-// counter, which after the first few tiles is always complete already.  Every CTA is co-resident
-// (persistent grid) and producers wait for nothing, so the waits cannot deadlock; they trap on a
+// counter, which after the first few tiles is always complete already.  Producers wait for nothing
+// and the grid is launched COOPERATIVELY (the driver guarantees every CTA is resident, or refuses
+// the launch and the host falls back to the pre-pass), so the waits cannot deadlock; they trap on a
 // 4 s watchdog like the mbarriers.  Measured: neutral at Q=4096 (the chip is at its power cap: the
 // same joules take the same time wherever they are spent), a clear win for 257..2048 queries.
-template <int KMAX, bool NORMS_INSIDE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NORMS_INSIDE ? P_THREADS_NORM : P_THREADS, 1)
+template <int KMAX, int NORMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NORMS != NORMS_CACHED ? P_THREADS_NORM : P_THREADS, 1)
 cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                              const __grid_constant__ CUtensorMap tmap_g,
                              const float* __restrict__ g_inv_norm, int Q, int N, int num_kb, int k,
@@ -632,6 +675,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                              const uint4* __restrict__ g_rows, int vec_per_row, float eps,
                              float* __restrict__ norm_out, uint32_t* __restrict__ tile_rows_done,
                              int norm_ahead) {
+  constexpr bool NORMS_INSIDE = NORMS == NORMS_PRODUCERS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -641,6 +685,8 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto empty_bar = [&](int s) { return bars + 8u * (P_STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + ACC_STAGES + s); };
+  auto gnfull_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + 2 * ACC_STAGES + s); };
+  auto normdone_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + 3 * ACC_STAGES + s); };
   const uint32_t tmem_slot = bars + P_SMEM_BARS;
   float* gn_smem = reinterpret_cast<float*>(smem_gen + P_SMEM_TILES);
   volatile uint32_t* tmem_slot_gen =
@@ -669,7 +715,9 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);                        // one multicast tcgen05.commit
       mbar_init(tempty_bar(s), 2 * (EPI_THREADS / 32));  // 4 epilogue warps of each CTA (leader's copy)
+      mbar_init(gnfull_bar(s), 2 * (NORM_THREADS / 32)); // NORMS_FUSED: 4 norm warps of each CTA
     }
+    for (int s = 0; s < P_STAGES; ++s) mbar_init(normdone_bar(s), NORM_THREADS / 32);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
@@ -692,6 +740,8 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (int t = t0; t < t1; ++t) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 1100 + stage);
+          // fused norms: this CTA's norm warps have square-summed the stage's previous contents
+          if (NORMS == NORMS_FUSED) mbar_wait(normdone_bar(stage), phase ^ 1u, 1150 + stage);
           if (lane == 0) {
             const uint32_t a_dst = smem_base + stage * P_STAGE_BYTES;
             const uint32_t b_dst = a_dst + P_A_BYTES;
@@ -739,6 +789,45 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
             __syncwarp();
             if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
           }
+        }
+      }
+    }
+  } else if (NORMS == NORMS_FUSED && warp >= P_NORM_WARP0) {
+    // ===================== fused gallery norms (this CTA's half of every tile) ===============
+    // thread nt owns gallery row rank*128 + nt of the tile: one 128-byte slice per stage, read in
+    // logical chunk order (conflict-free, position independent — see the single-CTA kernel)
+    const int nt = threadIdx.x - P_NORM_WARP0 * 32;
+    const uint32_t peer = rank ^ 1u;
+    const bool f16 = is_f16 != 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t it = 0;
+    for (int u = cluster_id; u < total_units; u += num_clusters) {
+      const int chunk = u / m_pairs;
+      const int t0 = chunk * tiles_per_chunk;
+      const int t1 = min(t0 + tiles_per_chunk, n_tiles);
+      for (int t = t0; t < t1; ++t, ++it) {
+        float sa = 0.f, sb = 0.f;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase, 1500 + stage);   // the stage's MMAs have retired
+          const uint4* r = reinterpret_cast<const uint4*>(smem_gen + stage * P_STAGE_BYTES + P_A_BYTES + nt * 128);
+          if (f16) norm_row_sums<true>(r, nt, sa, sb);
+          else     norm_row_sums<false>(r, nt, sa, sb);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(normdone_bar(stage));   // the producer may refill the stage
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        // gn[as] is free: this tile's MMAs only started after both epilogues drained the tile that
+        // used accumulator stage `as` (and its norms) before
+        const uint32_t as = it & 1u;
+        const float inv = 1.0f / fmaxf(sqrtf(sa + sb), eps);
+        float* mine = gn_smem + as * BLOCK_N + static_cast<int>(rank) * P_B_ROWS + nt;
+        *mine = inv;
+        st_shared_cluster_f32(mapa_rank(smem_u32(mine), peer), inv);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(mapa_rank(gnfull_bar(as), 0));
+          mbar_arrive_cluster(mapa_rank(gnfull_bar(as), 1));
         }
       }
     }
@@ -807,7 +896,9 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         const int n0 = t * BLOCK_N;
         float* gn = gn_smem + as * BLOCK_N;
-        {
+        if (NORMS == NORMS_FUSED) {
+          mbar_wait_cluster(gnfull_bar(as), aphase, 1600 + as);   // both halves' norms have landed
+        } else {
           const int c0 = n0 + et, c1 = n0 + et + EPI_THREADS;
           if (NORMS_INSIDE) {
             if (et == 0) *stream_pos = (u / num_clusters) * tiles_per_chunk + (t - t0);
@@ -823,8 +914,8 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
             gn[et] = c0 < N ? __ldg(g_inv_norm + c0) : 0.0f;
             gn[et + EPI_THREADS] = c1 < N ? __ldg(g_inv_norm + c1) : 0.0f;
           }
+          named_bar_sync(1, EPI_THREADS);
         }
-        named_bar_sync(1, EPI_THREADS);
         mbar_wait(tfull_bar(as), aphase, 1400 + as);
         tcgen05_fence_after();
         const int n_valid = min(BLOCK_N, N - n0);
@@ -878,10 +969,8 @@ Plan make_plan_pair(int64_t Q, int64_t N) {
     const double cost = static_cast<double>(waves) * (tpc + 0.35);
     if (cost < best_cost - 1e-9) { best_cost = cost; best_tpc = tpc; }
   }
-  if (const char* e = getenv("IRR_TILES_PER_CHUNK")) {
-    const int v = atoi(e);
-    if (v >= 1 && v <= p.n_tiles) best_tpc = v;
-  }
+  const int forced = knobs().tiles_per_chunk;
+  if (forced >= 1 && forced <= p.n_tiles) best_tpc = forced;
   p.tiles_per_chunk = best_tpc;
   p.n_chunks = (p.n_tiles + best_tpc - 1) / best_tpc;
   const long long units = 1ll * p.n_chunks * p.m_tiles;
@@ -889,46 +978,95 @@ Plan make_plan_pair(int64_t Q, int64_t N) {
   return p;
 }
 
-// Which kernel serves a batch of Q queries (measured on B200 at N=1M, D=1536, see
-// profiles/r01_notes.md): the CTA-pair kernel for more than three query tiles (tensor-bound regime;
-// it moves a third less data per flop) and for 129..256 queries with cached norms (one pair streams
-// the gallery once); the single-CTA kernel otherwise.  IRR_NO_PAIR=1 / IRR_FORCE_PAIR=1 are
-// measurement knobs for profiles/, not an API.
+// Which kernel serves a batch of Q queries (measured on B200 at N=1M, D=1536, see profiles/):
+//   Q <= 128          single-CTA kernel (norm warps fused into the tile stream when uncached)
+//   129..256          CTA-pair kernel: one pair streams the gallery once
+//   257..384 cached   single-CTA kernel, three query tiles (a second pair would multiply 128 rows
+//                     of zeros)
+//   257..384 uncached CTA-pair kernel with fused norms (beats the norm pre-pass + three tiles)
+//   >= 385            CTA-pair kernel (it moves a third less data per flop)
 bool use_pair(int64_t Q, bool cached_norms) {
   if (Q <= BLOCK_M) return false;
-  const char* no = getenv("IRR_NO_PAIR");
-  if (no && no[0] == '1') return false;
-  const char* force = getenv("IRR_FORCE_PAIR");
-  if (force && force[0] == '1') return true;
-  if (Q <= 2 * BLOCK_M) return cached_norms;
-  return Q > 3 * BLOCK_M;
+  if (knobs().no_pair) return false;
+  if (knobs().force_pair) return true;
+  if (Q > 2 * BLOCK_M && Q <= 3 * BLOCK_M) return !cached_norms && knobs().fused_pair;
+  return true;
 }
 
-// How many tiles the in-kernel norm producers may run ahead of their CTA's epilogue (see the
-// kernel).  IRR_NORM_AHEAD overrides (negative = unpaced); measurement knob, not an API.
-int norm_ahead_tiles() {
-  static int cached = []() {
-    const char* e = getenv("IRR_NORM_AHEAD");
-    return e ? atoi(e) : 2;
-  }();
-  return cached;
+// norm source of an uncached pair launch: grid-wide producers from three query-tile pairs on
+// (every pair recomputing the norms of the tiles it streams would cost 16x the arithmetic at
+// Q=4096), norms fused into the tile stream below (the tile stream outruns four producer warps per
+// CTA there: measured 512 queries 1.69 vs 1.66 ms with the pre-pass, 768 queries 2.14 vs 2.54 ms)
+int pair_norm_mode(bool cached, int m_pairs) {
+  if (cached) return NORMS_CACHED;
+  if (knobs().producers && m_pairs >= knobs().producers_min_pairs) return NORMS_PRODUCERS;
+  return knobs().fused_pair ? NORMS_FUSED : NORMS_CACHED;   // CACHED here = streaming pre-pass first
 }
 
-// norms_inside: gin is the (not yet filled) fp32[N] buffer the in-kernel producers write and the
-// epilogues read; tile_done is the zeroed per-tile row counter array
-template <int KMAX, bool NORMS_INSIDE>
+// cudaFuncSetAttribute once per (kernel instantiation, device), not once per call
+bool attr_needed(std::atomic<uint64_t>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  return (done.load(std::memory_order_relaxed) >> dev & 1ull) == 0;
+}
+void attr_set(std::atomic<uint64_t>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64)
+    done.fetch_or(1ull << dev, std::memory_order_relaxed);
+}
+
+// NORMS_PRODUCERS: gin is the (not yet filled) fp32[N] buffer the in-kernel producers write and the
+// epilogues read; tile_done is the zeroed per-tile row counter array.  That variant's epilogues
+// wait for producers in OTHER CTAs, so it is launched cooperatively: the driver either makes the
+// whole grid resident (also under MPS partitions, green contexts or with SMs held by kernels of
+// other streams) or refuses the launch — reported to the caller as *refused = true, which then
+// takes the pre-pass instead.  The other variants only wait inside their own cluster.
+template <int KMAX, int NORMS>
 irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, int64_t Q,
                        int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
                        uint32_t* row_floor, bool f16, const void* g, float eps, uint32_t* tile_done,
-                       cudaStream_t st) {
-  auto kern = cosine_topk_bf16_pair_kernel<KMAX, NORMS_INSIDE>;
-  IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
+                       cudaStream_t st, bool* refused) {
+  auto kern = cosine_topk_bf16_pair_kernel<KMAX, NORMS>;
+  static std::atomic<uint64_t> attr_done{0};
+  if (attr_needed(attr_done)) {
+    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
+    attr_set(attr_done);
+  }
   const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
+  const int threads = NORMS != NORMS_CACHED ? P_THREADS_NORM : P_THREADS;
+  if (NORMS == NORMS_PRODUCERS) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = P_SMEM_ALLOC;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    profile_mark_start(st);
+    const cudaError_t e = cudaLaunchKernelEx(
+        &cfg, kern, tq, tg, gin, static_cast<int>(Q), static_cast<int>(N), num_kb, static_cast<int>(k),
+        p.m_tiles, p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi, row_floor, f16 ? 1 : 0,
+        static_cast<const uint4*>(g), D * 2 / 16, eps, const_cast<float*>(gin), tile_done,
+        knobs().norm_ahead);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources ||
+        e == cudaErrorNotSupported) {
+      cudaGetLastError();
+      profile_mark_stop(st);
+      *refused = true;
+      return IRR_OK;
+    }
+    profile_mark_stop(st);
+    if (e != cudaSuccess) return static_cast<irr_status>(static_cast<int>(e));
+    return IRR_OK;
+  }
   profile_mark_start(st);
-  kern<<<p.grid, NORMS_INSIDE ? P_THREADS_NORM : P_THREADS, P_SMEM_ALLOC, st>>>(
+  kern<<<p.grid, threads, P_SMEM_ALLOC, st>>>(
       tq, tg, gin, static_cast<int>(Q), static_cast<int>(N), num_kb, k, p.m_tiles, p.n_tiles,
       p.tiles_per_chunk, p.n_chunks, pv, pi, row_floor, f16 ? 1 : 0, static_cast<const uint4*>(g),
-      D * 2 / 16, eps, const_cast<float*>(gin), tile_done, norm_ahead_tiles());
+      D * 2 / 16, eps, const_cast<float*>(gin), tile_done, knobs().norm_ahead);
   profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -952,40 +1090,62 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// [rows, cols] bf16 / fp16 row-major, tile = box_rows x 64 columns, 128-byte swizzle, zero fill OOB
+// [rows, cols] bf16 / fp16 row-major, tile = box_rows x 64 columns, 128-byte swizzle, zero fill OOB.
+// A tensor map is a pure function of (base, rows, cols, box, dtype): the last few are kept per host
+// thread, so a resident gallery searched again and again (and a static query buffer replayed from a
+// serving loop) does not pay the driver's encode call per search.
+struct TmapKey {
+  const void* base;
+  int64_t rows, cols;
+  uint32_t box_rows;
+  bool f16;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && box_rows == o.box_rows && f16 == o.f16;
+  }
+};
 bool encode_bf16_rows(CUtensorMap* m, const void* base, int64_t rows, int64_t cols,
                       uint32_t box_rows, bool f16 = false) {
+  constexpr int SLOTS = 8;
+  struct Slot { TmapKey key; CUtensorMap map; bool used; };
+  thread_local Slot cache[SLOTS] = {};
+  thread_local int next = 0;
+  const TmapKey key = {base, rows, cols, box_rows, f16};
+  for (int i = 0; i < SLOTS; ++i)
+    if (cache[i].used && cache[i].key == key) { *m = cache[i].map; return true; }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
   cuuint32_t box[2] = {BLOCK_K, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  Slot& s = cache[next];
+  next = (next + 1) % SLOTS;
+  s.key = key; s.map = *m; s.used = true;
+  return true;
 }
 
 // rows of the query TMA box: a whole 128-row tile, or for a single small batch just the rows
 // that exist (rounded up to the 8-row swizzle atom) — out-of-bounds rows cost TMA time
-int a_box_rows(int64_t Q, int MT = 1) {
-  return Q >= MT * BLOCK_M ? MT * BLOCK_M : static_cast<int>((Q + 7) / 8 * 8);
+int a_box_rows(int64_t Q) {
+  return Q >= BLOCK_M ? BLOCK_M : static_cast<int>((Q + 7) / 8 * 8);
 }
 
-// Two query tiles per unit (SC<2>) pay off where they remove the norm pre-pass: 129..256 queries
-// without cached norms (measured 0.81-0.89 ms vs 1.04-1.08 ms at N=1M; with cached norms the
-// CTA-pair kernel is faster there, and beyond 256 queries SC<2> is shared-memory-bandwidth bound).
-int tiles_per_unit(int64_t Q, bool cached_norms) {
-  return (!cached_norms && Q > BLOCK_M && Q <= 2 * BLOCK_M) ? 2 : 1;
-}
-
-template <int KMAX, bool WS, bool FN, int MT = 1>
+template <int KMAX, bool WS, bool FN>
 irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, const float* qin,
                   int64_t Q, int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
                   float* scores, float eps, uint32_t* row_floor, bool f16, cudaStream_t st) {
-  auto kern = cosine_topk_bf16_kernel<KMAX, WS, FN, MT>;
-  constexpr int SMEM_ALLOC = SC<MT>::ALLOC;
-  IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+  auto kern = cosine_topk_bf16_kernel<KMAX, WS, FN>;
+  constexpr int SMEM_ALLOC = SC::ALLOC;
+  static std::atomic<uint64_t> attr_done{0};
+  if (attr_needed(attr_done)) {
+    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    attr_set(attr_done);
+  }
   const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
   // a gallery streamed by a single query tile is read exactly once: do not let it displace the
   // query tiles in L2; with several query tiles the gallery tiles are the L2-shared operand
@@ -994,7 +1154,7 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
   kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(tq, tg, gin, qin, static_cast<int>(Q),
                                                 static_cast<int>(N), num_kb, k, p.m_tiles,
                                                 p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
-                                                scores, g_policy, eps, a_box_rows(Q, MT), row_floor,
+                                                scores, g_policy, eps, a_box_rows(Q), row_floor,
                                                 f16 ? 1 : 0);
   if (!WS) profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
@@ -1009,29 +1169,13 @@ size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
   // the caller may or may not pass cached norms: size for the larger of the two plans
   size_t parts = 0;
   for (int cached = 0; cached < 2; ++cached) {
-    const Plan p = use_pair(Q, cached) ? make_plan_pair(Q, N)
-                                       : make_plan(Q, N, tiles_per_unit(Q, cached));
+    const Plan p = use_pair(Q, cached) ? make_plan_pair(Q, N) : make_plan(Q, N);
     const size_t n = static_cast<size_t>(p.n_chunks) * Q * k;
     if (n > parts) parts = n;
   }
   const size_t n_tiles = static_cast<size_t>((N + BLOCK_N - 1) / BLOCK_N);
   return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 +
          align_up(static_cast<size_t>(Q) * 4, 256) + align_up(n_tiles * 4, 256) + 256;
-}
-
-// In-kernel norm producers for uncached multi-tile batches (the pair kernel's NORMS_INSIDE
-// variant) instead of the streaming pre-pass.  IRR_NORMS_INSIDE=0 restores the pre-pass
-// (measurement knob for profiles/, not an API).
-int norms_inside_min_pairs() {
-  static int cached = []() {
-    const char* e = getenv("IRR_NORMS_MIN_PAIRS");
-    return e ? atoi(e) : 3;
-  }();
-  return cached;
-}
-bool norms_inside_enabled() {
-  const char* e = getenv("IRR_NORMS_INSIDE");
-  return !(e && e[0] == '0');
 }
 
 irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
@@ -1044,8 +1188,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   if (ws_bytes < bf16_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
   const bool cached = g_inv_norm != nullptr;
   const bool pair = use_pair(Q, cached);
-  const int mt = pair ? 1 : tiles_per_unit(Q, cached);
-  const Plan p = pair ? make_plan_pair(Q, N) : make_plan(Q, N, mt);
+  const Plan p = pair ? make_plan_pair(Q, N) : make_plan(Q, N);
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* gin_ws = reinterpret_cast<float*>(w);
   w += align_up(static_cast<size_t>(N) * 4, 256);
@@ -1057,51 +1200,55 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   uint32_t* row_floor = reinterpret_cast<uint32_t*>(w);
   w += align_up(static_cast<size_t>(Q) * 4, 256);
   uint32_t* tile_done = reinterpret_cast<uint32_t*>(w);
-  // with one or two query-tile pairs the tile stream consumes the gallery faster than four producer
-  // warps per CTA can normalise it (measured: 512 queries 1.69 vs 1.66 ms with the pre-pass, 768
-  // queries 2.14 vs 2.54 ms): from three pairs on the producers win
-  const bool inside = pair && !cached && p.m_tiles >= norms_inside_min_pairs() && norms_inside_enabled();
+  int mode = pair ? pair_norm_mode(cached, p.m_tiles) : NORMS_CACHED;
   // one memset: the rows' shared floors and (if used) the per-tile norm counters
   IRR_CUDA_TRY(cudaMemsetAsync(
       row_floor, 0,
-      inside ? align_up(static_cast<size_t>(Q) * 4, 256) + static_cast<size_t>(p.n_tiles) * 4
-             : static_cast<size_t>(Q) * 4,
+      mode == NORMS_PRODUCERS ? align_up(static_cast<size_t>(Q) * 4, 256) + static_cast<size_t>(p.n_tiles) * 4
+                              : static_cast<size_t>(Q) * 4,
       st));
 
-  // single query tile and no cached norms: fuse the gallery norms into the tile stream;
-  // otherwise the norms come from the caller's cache or from one streaming pre-pass
-  // fuse the gallery norms into the tile stream when every gallery tile has exactly one consumer
-  const bool fuse = !cached && !pair && p.m_tiles == 1;
-  const float* gin = g_inv_norm;
-  if (inside) {
-    gin = gin_ws;   // written by the kernel's own norm producers
-  } else if (!gin && !fuse) {
-    irr_status s = row_inv_norms(g, N, D, dt, eps, gin_ws, st);
-    if (s != IRR_OK) return s;
-    gin = gin_ws;
-  }
   CUtensorMap tq, tg;
-  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q, mt), f16) ||
+  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q), f16) ||
       !encode_bf16_rows(&tg, g, N, D, pair ? P_B_ROWS : BLOCK_N, f16))
     return IRR_ERR_UNSUPPORTED_DEVICE;
-  irr_status s;
+  irr_status s = IRR_OK;
   if (pair) {
-#define IRR_LAUNCH_PAIR(KM, NI) \
-  s = launch_pair<KM, NI>(tq, tg, gin, Q, N, D, k, p, pv, pi, row_floor, f16, g, eps, tile_done, st)
-    if (inside) { if (k <= 4) IRR_LAUNCH_PAIR(4, true); else IRR_LAUNCH_PAIR(16, true); }
-    else        { if (k <= 4) IRR_LAUNCH_PAIR(4, false); else IRR_LAUNCH_PAIR(16, false); }
+    const bool small_k = k <= 4;
+    bool refused = false;
+#define IRR_LAUNCH_PAIR(KM, NM, GIN) \
+  s = launch_pair<KM, NM>(tq, tg, GIN, Q, N, D, k, p, pv, pi, row_floor, f16, g, eps, tile_done, st, &refused)
+    if (mode == NORMS_PRODUCERS) {   // gin_ws is written by the kernel's own norm producers
+      if (small_k) IRR_LAUNCH_PAIR(4, NORMS_PRODUCERS, gin_ws); else IRR_LAUNCH_PAIR(16, NORMS_PRODUCERS, gin_ws);
+      if (s == IRR_OK && refused) mode = NORMS_CACHED;   // no co-resident grid: pre-pass instead
+    } else if (mode == NORMS_FUSED) {
+      if (small_k) IRR_LAUNCH_PAIR(4, NORMS_FUSED, nullptr); else IRR_LAUNCH_PAIR(16, NORMS_FUSED, nullptr);
+    }
+    if (s == IRR_OK && mode == NORMS_CACHED) {
+      const float* gin = g_inv_norm;
+      if (!gin) {
+        s = row_inv_norms(g, N, D, dt, eps, gin_ws, st);
+        if (s != IRR_OK) return s;
+        gin = gin_ws;
+      }
+      if (small_k) IRR_LAUNCH_PAIR(4, NORMS_CACHED, gin); else IRR_LAUNCH_PAIR(16, NORMS_CACHED, gin);
+    }
 #undef IRR_LAUNCH_PAIR
   } else {
-    // (KMAX, fused norms, query tiles per unit) -> instantiation
-#define IRR_LAUNCH_SC(KM, FN, MTV)                                                              \
-  s = launch<KM, false, FN, MTV>(tq, tg, FN ? nullptr : gin, nullptr, Q, N, D, k, p, pv, pi,    \
-                                 nullptr, eps, row_floor, f16, st)
-    if (mt == 2) {  // only chosen without cached norms: always the fused-norm variant
-      if (k <= 4) IRR_LAUNCH_SC(4, true, 2); else IRR_LAUNCH_SC(16, true, 2);
-    } else {
-      if (fuse) { if (k <= 4) IRR_LAUNCH_SC(4, true, 1); else IRR_LAUNCH_SC(16, true, 1); }
-      else      { if (k <= 4) IRR_LAUNCH_SC(4, false, 1); else IRR_LAUNCH_SC(16, false, 1); }
+    // fuse the gallery norms into the tile stream when every gallery tile has exactly one consumer;
+    // otherwise they come from the caller's cache or from one streaming pre-pass
+    const bool fuse = !cached && p.m_tiles == 1;
+    const float* gin = g_inv_norm;
+    if (!gin && !fuse) {
+      s = row_inv_norms(g, N, D, dt, eps, gin_ws, st);
+      if (s != IRR_OK) return s;
+      gin = gin_ws;
     }
+#define IRR_LAUNCH_SC(KM, FN)                                                                   \
+  s = launch<KM, false, FN>(tq, tg, FN ? nullptr : gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, \
+                            eps, row_floor, f16, st)
+    if (fuse) { if (k <= 4) IRR_LAUNCH_SC(4, true); else IRR_LAUNCH_SC(16, true); }
+    else      { if (k <= 4) IRR_LAUNCH_SC(4, false); else IRR_LAUNCH_SC(16, false); }
 #undef IRR_LAUNCH_SC
   }
   if (s != IRR_OK) return s;

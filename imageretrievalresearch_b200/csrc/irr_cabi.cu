@@ -114,6 +114,14 @@ irr_status large_k_cosine_topk(const void* q, const void* g, const float* g_inv_
   return IRR_OK;
 }
 
+// test aid (irr_debug_occupy_sms): CTAs that hold shared memory and spin for a fixed time
+__global__ void occupy_kernel(unsigned long long ns) {
+  extern __shared__ uint8_t occupy_smem[];
+  if (threadIdx.x == 0) occupy_smem[0] = 1;
+  const uint64_t t0 = global_timer_ns();
+  while (global_timer_ns() - t0 < ns) __nanosleep(2000);
+}
+
 }  // namespace
 }  // namespace irr
 
@@ -126,6 +134,19 @@ int32_t irr_version(void) { return 100; }
 void irr_profile_next_topk(void* ev_start, void* ev_stop) {
   g_prof_start = static_cast<cudaEvent_t>(ev_start);
   g_prof_stop = static_cast<cudaEvent_t>(ev_stop);
+}
+
+irr_status irr_debug_occupy_sms(int32_t ctas, int32_t smem_bytes, int64_t nanoseconds,
+                                irr_stream_t stream) {
+  if (ctas < 1 || smem_bytes < 0 || smem_bytes > 227 * 1024 || nanoseconds < 0 ||
+      nanoseconds > 2000000000ll)
+    return IRR_ERR_INVALID_ARG;
+  IRR_CUDA_TRY(cudaFuncSetAttribute(occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    smem_bytes));
+  occupy_kernel<<<ctas, 32, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<unsigned long long>(nanoseconds));
+  IRR_LAUNCH_CHECK();
+  return IRR_OK;
 }
 
 const char* irr_status_string(irr_status s) {
@@ -156,7 +177,12 @@ irr_status irr_cosine_topk(const void* q, const void* g, const float* g_inv_norm
   if (Q < 0 || N < 0 || k < 1 || !out_val || !out_idx) return IRR_ERR_INVALID_ARG;
   if (k > IRR_MAX_K) return IRR_ERR_K_TOO_LARGE;
   if (Q == 0) return IRR_OK;
-  if (!q || (N > 0 && !g) || !workspace) return IRR_ERR_INVALID_ARG;
+  // an empty gallery shard (total rows < ranks) is not an error: all k slots are padding
+  if (N == 0)
+    return check_rows(q, D, dt, true) != IRR_OK
+               ? check_rows(q, D, dt, true)
+               : fill_padding(out_val, out_idx, Q * k, reinterpret_cast<cudaStream_t>(stream));
+  if (!q || !g || !workspace) return IRR_ERR_INVALID_ARG;
   irr_status s = check_rows(q, D, dt, true);
   if (s != IRR_OK) return s;
   s = check_rows(g, D, dt, true);

@@ -289,6 +289,39 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
+// wait on a LOCAL mbarrier whose arrivals come from both CTAs of the cluster and publish data
+// the peer wrote into this CTA's shared memory (acquire at cluster scope)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity, int tag) {
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (global_timer_ns() - t0 > 4000000000ull) {
+      printf("irr_b200: mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, tag, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  mbar_wait_cluster_slow(bar, parity, tag);
+}
+// fp32 store into the shared memory of any CTA of the cluster (address from mapa_rank)
+__device__ __forceinline__ void st_shared_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
 // 2-D tiled load issued by either CTA of a pair; the bytes are accounted on the mbarrier at
 // `bar_cluster_addr`, which may live in the peer (leader) CTA
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, int c0, int c1,

@@ -29,6 +29,8 @@ irr_status merge_partials(const float* part_val, const int32_t* part_idx, int32_
 irr_status merge_candidates(const float* cand_val, int64_t val_rank_stride, const int64_t* cand_idx,
                             int64_t idx_rank_stride, int32_t G, int64_t Q, int32_t k,
                             float* out_val, int64_t* out_idx, cudaStream_t st);
+// every slot (-inf, -1): the result of searching an empty shard
+irr_status fill_padding(float* out_val, int64_t* out_idx, int64_t n, cudaStream_t st);
 irr_status topk_hits(const int64_t* idx, int64_t Q, int32_t k, const int64_t* q_label,
                      const int64_t* g_label, int64_t N, int64_t instance_offset, int64_t* out_hits,
                      cudaStream_t st);

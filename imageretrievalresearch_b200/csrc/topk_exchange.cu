@@ -25,9 +25,15 @@
 // half of n-1) only after its merge n, i.e. after every peer pushed n, which every peer does after
 // its own merge n-1.
 //
-// Deadlock freedom: a CTA only ever waits for REMOTE pushes; a push waits for nothing.  The fused
-// kernel keeps its grid small enough (<= 2 CTAs per SM) to be co-resident, so the push of a rank is
-// never queued behind its own spinning CTAs.  Every wait has a watchdog (trap, never a hung GPU).
+// Deadlock freedom: a CTA only ever waits for pushes, and a push waits for nothing — but every CTA
+// of the fused kernel also waits for its OWN rank's flag, which is published by the last CTA of the
+// same grid to finish pushing.  The whole grid therefore has to be resident at once: it is sized
+// from cudaOccupancyMaxActiveBlocksPerMultiprocessor (not from an assumed register count) and
+// launched COOPERATIVELY, so the driver either co-schedules all of it — also next to kernels of
+// other streams, under MPS partitions or green contexts — or refuses the launch, in which case the
+// call is issued as the push kernel followed by the wait+merge kernel (stream order then
+// guarantees the push has finished before any CTA waits).  Every wait has a watchdog (trap, never a
+// hung GPU).
 #include <stdlib.h>
 
 #include "irr_common.cuh"
@@ -164,7 +170,7 @@ __device__ __forceinline__ void merge_phase(const uint8_t* mine, int G, int64_t 
 
 // mode: IRR_XCHG_FUSED = push + wait + merge, IRR_XCHG_MERGE = wait + merge of the epoch already pushed
 template <int KMAX>
-__global__ void __launch_bounds__(XT)
+__global__ void __launch_bounds__(XT, 2)
 exchange_merge_kernel(const float* __restrict__ lv, const int64_t* __restrict__ li,
                       const __grid_constant__ Peers peers, int G, int rank, int64_t Q, int k,
                       const __grid_constant__ XGeom x, int mode, unsigned long long timeout_ns,
@@ -194,6 +200,17 @@ __global__ void __launch_bounds__(32)
 exchange_wait_kernel(const uint8_t* __restrict__ mine, int G, unsigned long long timeout_ns) {
   const uint32_t epoch = __ldcg(reinterpret_cast<const uint32_t*>(mine + X_STATE));
   wait_phase(mine, G, epoch, timeout_ns);
+}
+
+// CTAs of `kern` (XT threads, no dynamic shared memory) the current device holds at once
+template <typename K>
+int resident_ctas(K kern) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, XT, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  return per_sm * num_sms();
 }
 
 unsigned long long exchange_timeout_ns() {
@@ -227,7 +244,11 @@ irr_status topk_exchange_merge(const float* local_val, const int64_t* local_idx,
   }
   const XGeom x = make_geom(G, Q, k, buf_bytes);
   const unsigned long long tmo = exchange_timeout_ns();
-  const int cap = 2 * num_sms();   // co-resident by construction (8 such CTAs fit one SM)
+  // CTAs of the fused kernel that fit the device at once (queried once per instantiation)
+  static const int resident4 = resident_ctas(exchange_merge_kernel<4>);
+  static const int resident16 = resident_ctas(exchange_merge_kernel<16>);
+  const int resident = k <= 4 ? resident4 : resident16;
+  const int cap = resident < 2 * num_sms() ? resident : 2 * num_sms();
   const int64_t push_ctas = static_cast<int64_t>((x.n + XT - 1) / XT);
   const int64_t merge_ctas = (Q + XW - 1) / XW;
   auto clamp = [&](int64_t v) { return static_cast<int>(v < 1 ? 1 : (v > cap ? cap : v)); };
@@ -247,12 +268,43 @@ irr_status topk_exchange_merge(const float* local_val, const int64_t* local_idx,
                                            x.slot_bytes, x.idx_off, G, Q, k, out_val, out_idx, st);
   }
   const int grid = clamp(mode == IRR_XCHG_FUSED && push_ctas > merge_ctas ? push_ctas : merge_ctas);
+  if (mode == IRR_XCHG_FUSED) {
+    // cooperative: all CTAs resident, or the launch is refused (then: push kernel + merge kernel)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(XT);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const long long q64 = Q;
+    const cudaError_t e =
+        k <= 4 ? cudaLaunchKernelEx(&cfg, exchange_merge_kernel<4>, local_val, local_idx, peers,
+                                    static_cast<int>(G), static_cast<int>(rank), static_cast<int64_t>(q64),
+                                    static_cast<int>(k), x, static_cast<int>(mode), tmo, out_val, out_idx)
+               : cudaLaunchKernelEx(&cfg, exchange_merge_kernel<16>, local_val, local_idx, peers,
+                                    static_cast<int>(G), static_cast<int>(rank), static_cast<int64_t>(q64),
+                                    static_cast<int>(k), x, static_cast<int>(mode), tmo, out_val, out_idx);
+    if (e == cudaSuccess) return IRR_OK;
+    if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorLaunchOutOfResources &&
+        e != cudaErrorNotSupported)
+      return static_cast<irr_status>(static_cast<int>(e));
+    cudaGetLastError();
+    exchange_push_kernel<<<clamp(push_ctas), XT, 0, st>>>(local_val, local_idx, peers, G, rank, x);
+    IRR_LAUNCH_CHECK();
+    mode = IRR_XCHG_MERGE;
+  }
+  // wait + merge only: a CTA waits for pushes of OTHER grids (this rank's own push has completed in
+  // stream order), so residency does not matter
+  const int mgrid = clamp(merge_ctas);
   if (k <= 4)
-    exchange_merge_kernel<4><<<grid, XT, 0, st>>>(local_val, local_idx, peers, G, rank, Q, k, x, mode,
-                                                  tmo, out_val, out_idx);
+    exchange_merge_kernel<4><<<mgrid, XT, 0, st>>>(local_val, local_idx, peers, G, rank, Q, k, x, mode,
+                                                   tmo, out_val, out_idx);
   else
-    exchange_merge_kernel<16><<<grid, XT, 0, st>>>(local_val, local_idx, peers, G, rank, Q, k, x,
-                                                   mode, tmo, out_val, out_idx);
+    exchange_merge_kernel<16><<<mgrid, XT, 0, st>>>(local_val, local_idx, peers, G, rank, Q, k, x,
+                                                    mode, tmo, out_val, out_idx);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
 }

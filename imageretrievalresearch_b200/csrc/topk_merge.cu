@@ -117,7 +117,27 @@ topk_hits_kernel(const int64_t* __restrict__ idx, int64_t Q, int k,
   }
 }
 
+// an empty gallery shard: every slot is padding
+__global__ void __launch_bounds__(256)
+fill_padding_kernel(float* __restrict__ out_val, int64_t* __restrict__ out_idx, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    out_val[i] = kNegInf;
+    out_idx[i] = -1;
+  }
+}
+
 }  // namespace
+
+irr_status fill_padding(float* out_val, int64_t* out_idx, int64_t n, cudaStream_t st) {
+  if (n <= 0) return IRR_OK;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  fill_padding_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(out_val, out_idx, n);
+  IRR_LAUNCH_CHECK();
+  return IRR_OK;
+}
 
 irr_status merge_partials(const float* part_val, const int32_t* part_idx, int32_t S, int64_t Q,
                           int32_t k, const void* q, int32_t D, irr_dtype dt, float eps,

@@ -6,20 +6,24 @@
 //   the logged paired cosine scores         train/train_efficient_cos_con_ce_loss.py:377-382
 // and their autograd backward (closed forms: SURVEY.md §A.1).
 //
-// HBM-bound design: every input byte crosses L2->SM exactly once.  A group of four warps owns one
-// row triplet at a time (up to eight groups per CTA, one CTA per SM); the group's first lane stages
-// the three rows into the group's shared-memory slot with 1-D bulk async copies (cp.async.bulk,
-// completion on an mbarrier) one row ahead of the arithmetic; each thread reduces seven sums over
-// its 128-bit vectors (LDS.128 + shuffles + a fixed-order add of the four warp partials), every
-// thread derives the four loss terms and seven gradient coefficients from the same sums, and the
-// group streams dq/dp/dn straight from the staged rows with 128-bit stores.  (One warp per row —
-// the first version — left 1.5 warps per scheduler: ncu showed the kernel bound by its own
-// instruction latency at 19 % issue utilisation, not by HBM.)  Each gradient is a per-row linear
-// combination of the three rows:
+// HBM-bound design: every input byte crosses L2->SM exactly once.  A group of GW warps (1, 2 or 4:
+// as many as give every thread about three 128-bit vectors per row) owns one row triplet at a time
+// (up to 15 groups per CTA, one CTA per SM); the group's first lane stages the three rows into the
+// group's shared-memory ring with 1-D bulk async copies (cp.async.bulk, completion on an mbarrier)
+// up to three rows ahead of the arithmetic; each thread reduces seven sums over its vectors
+// (LDS.128 + shuffles), the warps' partials meet in a double-buffered scratch line behind ONE named
+// barrier per row, every warp adds them in the same fixed order and derives the four loss terms
+// and the gradient coefficients itself (a few dozen scalar instructions, cheaper than a second
+// barrier and a shared-memory round trip), and the group streams dq/dp/dn straight from the staged
+// rows with 128-bit stores.  (One warp per row — the first version — left 1.5 warps per scheduler;
+// four warps per row with three barriers — the second — spent a bf16 row's 9 KB on a latency chain:
+// 0.52 of HBM.)  Each gradient is a per-row linear combination of the three rows:
 //   dq = aqq*q + aqp*p + aqn*n     dp = app*p + aqp*q     dn = ann*n + aqn*q
 // Loss scalars: fixed row->group assignment, per-group partials, last-CTA-done fixed-order reduction
 // (deterministic; the sync word resets itself, see irr_b200.h).
 #include <stdlib.h>
+
+#include <atomic>
 
 #include "irr_common.cuh"
 #include "irr_kernels.h"
@@ -27,10 +31,9 @@
 namespace irr {
 namespace {
 
-constexpr int LSTAGES = 2;
-constexpr int GW = 4;            // warps that share one row triplet
-constexpr int GT = GW * 32;
-constexpr int MAX_GROUPS = 8;    // row-triplet slots (groups of GW warps) per CTA
+constexpr int MAX_STAGES = 4;    // rows a group keeps in flight (ring depth, chosen at launch)
+constexpr int MAX_GROUPS = 15;   // groups per CTA: one named barrier each (ids 1..15)
+constexpr int MAX_THREADS = 1024;
 constexpr int SMEM_BUDGET = 220 * 1024;
 
 struct Coef {
@@ -177,27 +180,30 @@ struct KParams {
   unsigned int* sync_word;
   float* partials;  // [gridDim.x * groups][4], 16-byte aligned
   int hints;        // measurement knob IRR_LOSS_HINTS: 1 = evict-first loads, 2 = streaming stores
+  int stages;       // ring depth per group (1..MAX_STAGES)
 };
 
-template <bool BF16, bool TRIPLET>
-__global__ void __launch_bounds__(MAX_GROUPS * GT, 1)
+template <bool BF16, bool TRIPLET, int GW>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 loss_fwd_bwd_kernel(const KParams P) {
+  constexpr int GT = GW * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const int groups = blockDim.x / GT;
-  const int grp = threadIdx.x / GT;   // row-triplet slot this thread's group owns
+  const int grp = threadIdx.x / GT;   // row-triplet ring this thread's group owns
   const int gt = threadIdx.x % GT;    // thread within the group
   const int gwarp = gt >> 5, lane = gt & 31;
+  const int stages = P.stages;
   constexpr int ROWS = TRIPLET ? 3 : 2;
   const uint32_t row_bytes = static_cast<uint32_t>(P.vec_per_row) * 16u;
   const uint32_t slot_bytes = ROWS * row_bytes;
-  // [groups][LSTAGES][ROWS][row_bytes] | mbarriers [groups][LSTAGES] | scratch [groups][GW+1][8]
-  uint8_t* my_slots = smem + static_cast<size_t>(grp) * LSTAGES * slot_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(groups) * LSTAGES * slot_bytes);
-  float* scratch = reinterpret_cast<float*>(bars + groups * LSTAGES) + grp * ((GW + 1) * 8);
-  const uint32_t bar0 = smem_u32(bars + grp * LSTAGES);
+  // [groups][stages][ROWS][row_bytes] | mbarriers [groups][stages] | scratch [groups][2][GW][8]
+  uint8_t* my_slots = smem + static_cast<size_t>(grp) * stages * slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(groups) * stages * slot_bytes);
+  float* scratch = reinterpret_cast<float*>(bars + groups * stages) + grp * (2 * GW * 8);
+  const uint32_t bar0 = smem_u32(bars + grp * stages);
 
   if (gt == 0) {
-    for (int s = 0; s < LSTAGES; ++s) mbar_init(bar0 + 8u * s, 1);
+    for (int s = 0; s < stages; ++s) mbar_init(bar0 + 8u * s, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -222,27 +228,25 @@ loss_fwd_bwd_kernel(const KParams P) {
   };
 
   if (gt == 0) {
-    for (int s = 0; s < LSTAGES; ++s) {
+    for (int s = 0; s < stages; ++s) {
       const int64_t row = gg + s * tg;
       if (row < P.B) issue(row, s);
     }
   }
 
-  float lsum[4] = {0.f, 0.f, 0.f, 0.f};   // meaningful in the group's first warp only
+  float lsum[4] = {0.f, 0.f, 0.f, 0.f};   // kept by the group's first warp only
   constexpr int VH = Vec<BF16>::H;
   const float2 neg1 = splat2(-1.0f);
-  float* coef_s = scratch + GW * 8;       // 8 floats: the row's gradient coefficients
-  int it = 0;
+  int it = 0, s = 0;
+  uint32_t parity = 0;
   for (int64_t row = gg; row < P.B; row += tg, ++it) {
-    const int s = it % LSTAGES;
-    const uint32_t parity = (it / LSTAGES) & 1;
     mbar_wait_parked(bar0 + 8u * s, parity, 500 + s);
     const uint4* sq = reinterpret_cast<const uint4*>(my_slots + static_cast<size_t>(s) * slot_bytes);
     const uint4* sp = sq + P.vec_per_row;
     const uint4* sn = sp + P.vec_per_row;
 
     // ---- seven sums: this thread's 16-byte vectors (even / odd elements in the two packed lanes),
-    // then the warp (warp_reduce8), then the group's four warps (first warp, fixed order) ----
+    // then the warp (warp_reduce8), then the group's warps (every warp, same fixed order) ----
     float2 aqq = splat2(0.f), app = aqq, ann = aqq, aqp = aqq, aqn = aqq, adp = aqq, adn = aqq;
     for (int v = gt; v < P.vec_per_row; v += GT) {
       float2 fq[VH], fp[VH], fn[VH];
@@ -264,17 +268,26 @@ loss_fwd_bwd_kernel(const KParams P) {
         }
       }
     }
+    // scratch line of this row (double-buffered by row parity: a warp that is already on the next
+    // row must not overwrite what a slower warp of the group is still adding up)
+    float* line = scratch + (it & 1) * (GW * 8);
     {
       const float part[8] = {aqq.x + aqq.y, app.x + app.y, ann.x + ann.y, aqp.x + aqp.y,
                              aqn.x + aqn.y, adp.x + adp.y, adn.x + adn.y, 0.f};
       const float r = warp_reduce8(part, lane);
-      if ((lane & 3) == 0) scratch[gwarp * 8 + (lane >> 2)] = r;
+      if ((lane & 3) == 0) line[gwarp * 8 + (lane >> 2)] = r;
     }
-    named_bar_sync(1 + grp, GT);
+    named_bar_sync(1 + grp, GT);   // the ONE barrier per row
+    // every thread of the group is past the previous row: its ring slot can be refilled
+    if (gt == 0 && it > 0) {
+      const int64_t next = row + static_cast<int64_t>(stages - 1) * tg;
+      if (next < P.B) issue(next, s == 0 ? stages - 1 : s - 1);
+    }
 
-    if (gwarp == 0) {
-      // order of the eight slots = warp_reduce8's value index: qq pp nn qp | qn dp dn -
-      const float4* sc = reinterpret_cast<const float4*>(scratch);
+    // order of the eight slots = warp_reduce8's value index: qq pp nn qp | qn dp dn -
+    RowOut o;
+    {
+      const float4* sc = reinterpret_cast<const float4*>(line);
       float4 a = sc[0], b = sc[1];
 #pragma unroll
       for (int w = 1; w < GW; ++w) {
@@ -283,19 +296,17 @@ loss_fwd_bwd_kernel(const KParams P) {
         b.x += d.x; b.y += d.y; b.z += d.z;
       }
       const RowSums S = {a.x, a.y, a.z, a.w, b.x, b.y, b.z};
-      RowOut o;
       if (TRIPLET) {
         o = triplet_row(S, P.m_cos, P.m_con, P.w);
       } else {
         const float y = __ldg(P.label + (P.label_count == 1 ? 0 : row));
         o = pair_row(S, P.kind, y, P.kind == IRR_LOSS_CONTRASTIVE ? P.m_con : P.m_cos, P.w[0]);
       }
+      if (gwarp == 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) lsum[j] += o.l[j];
-      if (lane == 0) {
-        float4* cs = reinterpret_cast<float4*>(coef_s);
-        cs[0] = make_float4(o.c.aqq, o.c.aqp, o.c.aqn, o.c.app);
-        cs[1] = make_float4(o.c.ann, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) lsum[j] += o.l[j];
+      }
+      if (gt == 0) {
         if (P.pair_cos) {
           const float nq = fmaxf(sqrtf(S.qq), P.pair_eps);
           P.pair_cos[row] = S.qp / (nq * fmaxf(sqrtf(S.pp), P.pair_eps));
@@ -310,10 +321,8 @@ loss_fwd_bwd_kernel(const KParams P) {
     }
 
     if (P.dq) {
-      named_bar_sync(1 + grp, GT);   // coefficients published
-      const float4 c0 = reinterpret_cast<const float4*>(coef_s)[0];
-      const float2 kqq = splat2(c0.x), kqp = splat2(c0.y), kqn = splat2(c0.z), kpp = splat2(c0.w);
-      const float2 knn = splat2(coef_s[4]);
+      const float2 kqq = splat2(o.c.aqq), kqp = splat2(o.c.aqp), kqn = splat2(o.c.aqn),
+                   kpp = splat2(o.c.app), knn = splat2(o.c.ann);
       uint4* gq = P.dq + row * P.vec_per_row;
       uint4* gp = P.dp + row * P.vec_per_row;
       uint4* gn = TRIPLET ? P.dn + row * P.vec_per_row : nullptr;
@@ -343,11 +352,7 @@ loss_fwd_bwd_kernel(const KParams P) {
         }
       }
     }
-
-    // the whole group is done with the slot (and with the scratch words) before it is refilled
-    named_bar_sync(1 + grp, GT);
-    const int64_t next = row + LSTAGES * tg;
-    if (gt == 0 && next < P.B) issue(next, s);
+    if (++s == stages) { s = 0; parity ^= 1u; }
   }
 
   // ---- deterministic reduction of the loss scalars: one partial per group (fixed row -> group
@@ -357,7 +362,7 @@ loss_fwd_bwd_kernel(const KParams P) {
     reinterpret_cast<float4*>(P.partials)[gg] = make_float4(lsum[0], lsum[1], lsum[2], lsum[3]);
   __syncthreads();
   __shared__ int is_last;
-  __shared__ float4 red[MAX_GROUPS * GW];
+  __shared__ float4 red[MAX_THREADS / 32];
   if (threadIdx.x == 0) {
     __threadfence();   // cumulative: covers the group leaders' partials ordered by the barrier
     const unsigned int prev = atomicAdd(P.sync_word, 1u);
@@ -453,34 +458,64 @@ loss_bwd_kernel(const BParams P) {
 }
 
 struct LaunchShape {
-  int groups, grid;
+  int gw, stages, groups, grid;
   size_t smem;
 };
 
-// row-triplet slots per CTA from the shared-memory budget, then spread the rows over the SMs
+// measurement knobs for profiles/ (environment, read once): IRR_LOSS_GW, IRR_LOSS_STAGES,
+// IRR_LOSS_HINTS — not an API
+struct LossKnobs { int gw, stages, hints; };
+const LossKnobs& loss_knobs() {
+  static const LossKnobs k = []() {
+    auto num = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    LossKnobs r;
+    r.gw = num("IRR_LOSS_GW", 0);
+    r.stages = num("IRR_LOSS_STAGES", 0);
+    r.hints = num("IRR_LOSS_HINTS", 1);   // evict-first loads measured +3 % (profiles/r01_notes.md)
+    return r;
+  }();
+  return k;
+}
+
+// Warps per row: as many as leave every thread about three 128-bit vectors per row (a bf16 row of
+// 1536 elements is 192 vectors: two warps; the fp32 row 384: four).  Ring depth and groups per CTA
+// from the shared-memory budget, then spread the rows over the SMs.
 bool shape_for(int64_t B, int32_t D, irr_dtype dt, bool triplet, LaunchShape* s) {
   const size_t row_bytes = static_cast<size_t>(D) * dtype_bytes(dt);
-  const size_t per_group = LSTAGES * (triplet ? 3 : 2) * row_bytes + LSTAGES * 8 + (GW + 1) * 8 * sizeof(float);
-  int gmax = static_cast<int>(SMEM_BUDGET / per_group);
-  if (gmax < 1) return false;
-  if (gmax > MAX_GROUPS) gmax = MAX_GROUPS;
+  const int vec_per_row = static_cast<int>(row_bytes / 16);
+  int gw = vec_per_row >= 4 * 96 ? 4 : vec_per_row >= 2 * 96 ? 2 : 1;
+  if (loss_knobs().gw == 1 || loss_knobs().gw == 2 || loss_knobs().gw == 4) gw = loss_knobs().gw;
   const int sms = num_sms();
-  int64_t want = (B + sms - 1) / sms;  // rows per SM if every SM takes part
-  int groups = static_cast<int>(want < 1 ? 1 : (want > gmax ? gmax : want));
+  const int64_t rows_per_sm = (B + sms - 1) / sms;  // if every SM takes part
+  const int gcap = MAX_THREADS / (gw * 32) < MAX_GROUPS ? MAX_THREADS / (gw * 32) : MAX_GROUPS;
+  auto per_group = [&](int stages) {
+    return static_cast<size_t>(stages) * ((triplet ? 3 : 2) * row_bytes + 8) + 2 * gw * 8 * sizeof(float);
+  };
+  // deepest ring that still leaves room for enough groups to keep every row of the SM's share in
+  // some group's hands (few rows per SM: more groups matter more than depth)
+  int stages = 3;
+  if (loss_knobs().stages >= 2 && loss_knobs().stages <= MAX_STAGES) stages = loss_knobs().stages;
+  while (stages > 2 && static_cast<int64_t>(SMEM_BUDGET / per_group(stages)) < (rows_per_sm < gcap ? rows_per_sm : gcap))
+    --stages;
+  int gmax = static_cast<int>(SMEM_BUDGET / per_group(stages));
+  if (gmax < 1) return false;
+  if (gmax > gcap) gmax = gcap;
+  int groups = static_cast<int>(rows_per_sm < 1 ? 1 : (rows_per_sm > gmax ? gmax : rows_per_sm));
   int64_t grid = (B + groups - 1) / groups;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
+  s->gw = gw;
+  s->stages = stages;
   s->groups = groups;
   s->grid = static_cast<int>(grid);
-  s->smem = static_cast<size_t>(groups) * per_group;
+  s->smem = static_cast<size_t>(groups) * per_group(stages);
   return true;
 }
 
 }  // namespace
 
 size_t loss_workspace_bytes(int64_t, int32_t, irr_dtype) {
-  // sync word (padded) + per-group partials for the largest launch shape (sized generously: the
-  // previous per-warp layout's 16 entries per SM)
+  // sync word (padded) + one float4 partial per group for the largest launch shape
   return 256 + static_cast<size_t>(num_sms()) * 16 * 4 * sizeof(float);
 }
 
@@ -511,23 +546,35 @@ irr_status loss_fwd_bwd(const LossArgs& a, void* ws, size_t ws_bytes, cudaStream
   P.dn = static_cast<uint4*>(a.dn);
   P.sync_word = static_cast<unsigned int*>(ws);
   P.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
-  {
-    const char* e = getenv("IRR_LOSS_HINTS");
-    P.hints = e ? atoi(e) : 1;   // evict-first loads measured +3 % (profiles/r01_notes.md)
-  }
+  P.hints = loss_knobs().hints;
+  P.stages = sh.stages;
 
-#define IRR_LAUNCH_LOSS(BF, TR)                                                                   \
+  // the attribute is set to the budget once per instantiation and device, not per call
+#define IRR_LAUNCH_LOSS(BF, TR, GWV)                                                              \
   do {                                                                                            \
-    auto kern = loss_fwd_bwd_kernel<BF, TR>;                                                      \
-    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                      static_cast<int>(sh.smem)));                                \
-    kern<<<sh.grid, sh.groups * GT, sh.smem, st>>>(P);                                             \
+    auto kern = loss_fwd_bwd_kernel<BF, TR, GWV>;                                                 \
+    static std::atomic<uint64_t> attr_done{0};                                                    \
+    int dev = 0;                                                                                  \
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ||                             \
+        !(attr_done.load(std::memory_order_relaxed) >> dev & 1ull)) {                             \
+      IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                        SMEM_BUDGET));                                            \
+      if (dev >= 0 && dev < 64) attr_done.fetch_or(1ull << dev, std::memory_order_relaxed);       \
+    }                                                                                             \
+    kern<<<sh.grid, sh.groups * (GWV) * 32, sh.smem, st>>>(P);                                    \
+  } while (0)
+#define IRR_LAUNCH_LOSS_GW(BF, TR)                                                                \
+  do {                                                                                            \
+    if (sh.gw == 4) IRR_LAUNCH_LOSS(BF, TR, 4);                                                   \
+    else if (sh.gw == 2) IRR_LAUNCH_LOSS(BF, TR, 2);                                              \
+    else IRR_LAUNCH_LOSS(BF, TR, 1);                                                              \
   } while (0)
   if (a.dt == IRR_BF16) {
-    if (triplet) IRR_LAUNCH_LOSS(true, true); else IRR_LAUNCH_LOSS(true, false);
+    if (triplet) IRR_LAUNCH_LOSS_GW(true, true); else IRR_LAUNCH_LOSS_GW(true, false);
   } else {
-    if (triplet) IRR_LAUNCH_LOSS(false, true); else IRR_LAUNCH_LOSS(false, false);
+    if (triplet) IRR_LAUNCH_LOSS_GW(false, true); else IRR_LAUNCH_LOSS_GW(false, false);
   }
+#undef IRR_LAUNCH_LOSS_GW
 #undef IRR_LAUNCH_LOSS
   IRR_LAUNCH_CHECK();
   return IRR_OK;

@@ -205,9 +205,10 @@ class CapturedSearch:
     """
 
     def __init__(self, search_fn, num_queries: int, dim: int, k: int, dtype: torch.dtype,
-                 device: torch.device, warmup: int = 2) -> None:
+                 device: torch.device, warmup: int = 2, on_release=None) -> None:
         self.queries = torch.zeros((num_queries, dim), dtype=dtype, device=device)
         self.k = k
+        self._on_release = on_release
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
@@ -219,13 +220,35 @@ class CapturedSearch:
         with torch.cuda.graph(self.graph):
             self.result = search_fn(self.queries, k)
 
-    def __call__(self, queries: Optional[torch.Tensor] = None) -> TopK:
+    def __call__(self, queries: Optional[torch.Tensor] = None, k: Optional[int] = None) -> TopK:
         """Replay.  `queries` (optional) is copied into the static input first; the returned TopK
-        tensors are the graph's static outputs, overwritten by the next replay."""
+        tensors are the graph's static outputs, overwritten by the next replay.  `k`, if given,
+        must be the captured k (lets a replay stand in wherever a ``search(queries, k)`` is taken)."""
+        if k is not None and k != self.k:
+            raise ValueError(f"this search was captured for k={self.k}, not k={k}")
         if queries is not None:
             self.queries.copy_(queries)
         self.graph.replay()
         return self.result
+
+    def release(self) -> None:
+        """Drop the graph (and tell the owner that its baked-in pointers are no longer live)."""
+        if self.graph is not None:
+            self.graph = None
+            self.result = None
+            if self._on_release is not None:
+                self._on_release()
+                self._on_release = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    # the TopK this returns is overwritten by the next replay (SearchPipeline orders its read-back
+    # of batch n before the replay for batch n+1 when it sees this)
+    static_outputs = True
 
 
 class SearchPipeline:
@@ -240,7 +263,14 @@ class SearchPipeline:
     """
 
     def __init__(self, search_fn, num_queries: int, dim: int, k: int, dtype: torch.dtype,
-                 device: torch.device, depth: int = 2) -> None:
+                 device: torch.device, depth: int = 2, static_outputs: Optional[bool] = None) -> None:
+        """static_outputs: the search returns the SAME output tensors on every call (a
+        CapturedSearch replay) — the next search may then only start once the previous batch's
+        read-back has finished.  Default: detected from ``search_fn.static_outputs``."""
+        if static_outputs is None:
+            static_outputs = bool(getattr(search_fn, "static_outputs", False))
+        self.static_outputs = static_outputs
+        self._last_r: Optional[int] = None
         if depth < 2:
             raise ValueError("depth >= 2: one batch in flight while the next is being copied")
         device = torch.device(device)
@@ -272,12 +302,16 @@ class SearchPipeline:
             self._q[s].copy_(q_host, non_blocking=True)
             self._landed[s].record(self._h2d)
         cur.wait_event(self._landed[s])
+        if self.static_outputs and self._last_r is not None:
+            cur.wait_event(self._back[self._last_r])     # the outputs about to be overwritten are on the host
+        self._last_r = r
         res = self.search_fn(self._q[s], self.k)
         self._searched[s].record(cur)
         self._d2h.wait_event(self._searched[s])
         with torch.cuda.stream(self._d2h):
-            res.values.record_stream(self._d2h)
-            res.indices.record_stream(self._d2h)
+            if not self.static_outputs:
+                res.values.record_stream(self._d2h)
+                res.indices.record_stream(self._d2h)
             self._v[r].copy_(res.values, non_blocking=True)
             self._i[r].copy_(res.indices, non_blocking=True)
             self._back[r].record(self._d2h)
@@ -287,6 +321,7 @@ class SearchPipeline:
         for every batch of ``host_batches`` (pinned host ``[Q, D]`` tensors), in order."""
         pending = []          # result slots in flight, oldest first
         n = 0
+        self._last_r = None
         for q_host in host_batches:
             if len(pending) == self.depth:               # hand out the oldest batch first
                 r = pending.pop(0)

@@ -100,16 +100,29 @@ class PeerExchange:
         self.mapping = mapping
         self._imported: List[int] = []
         self.handle = None
+        if mapping not in ("symm", "ipc"):
+            raise ValueError("mapping must be 'symm' or 'ipc'")
+        # step 1, local: allocate.  Every rank reports the outcome BEFORE anybody enters the
+        # collective mapping step, so an allocation failure on one rank cannot leave the others
+        # waiting in a rendezvous it never joins.
+        err = None
+        try:
+            if mapping == "symm":
+                import torch.distributed._symmetric_memory as symm_mem
+                self.buf = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=device)
+            else:
+                self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        except Exception as e:  # noqa: BLE001
+            err = e
+        if not _agree(err is None, self.group, device):
+            raise RuntimeError(f"peer exchange buffer ({mapping}) could not be allocated on every rank"
+                               + (f": {type(err).__name__}: {err}" if err is not None else ""))
+        # step 2, collective: map every rank's buffer into this process
         if mapping == "symm":
-            import torch.distributed._symmetric_memory as symm_mem
-            self.buf = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=device)
             self.handle = symm_mem.rendezvous(self.buf, self.group)
             self.ptrs: List[int] = [int(p) for p in self.handle.buffer_ptrs]
-        elif mapping == "ipc":
-            self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
-            self.ptrs = self._map_ipc()
         else:
-            raise ValueError("mapping must be 'symm' or 'ipc'")
+            self.ptrs = self._map_ipc()
         if len(self.ptrs) != self.world or self.ptrs[self.rank] != self.buf.data_ptr():
             raise RuntimeError("peer mapping returned an unexpected pointer table")
 
@@ -207,6 +220,7 @@ class ShardedGallery:
         self._peer_failed = False
         self.exchange_error: Optional[str] = None
         self._lagged: Optional[Tuple[int, int]] = None   # (Q, k) of the search whose result is pending
+        self._live_captures = 0      # CUDA graphs holding this exchange buffer's mapped pointers
         lo, hi = shard_bounds(total_rows, self.world, self.rank)
         if local_embeddings.shape[0] != hi - lo:
             raise ValueError(
@@ -245,6 +259,14 @@ class ShardedGallery:
             return self._peer
         need = max(2 * _ops.topk_exchange_bytes(self.world, Q, k), 1 << 20)
         if self._peer is not None:
+            if self._live_captures > 0:
+                # a captured graph has the current buffers' peer pointers baked into its kernel
+                # arguments: replaying it after the buffers were unmapped would store into freed
+                # memory on every rank
+                raise RuntimeError(
+                    f"a search with Q={Q}, k={k} needs a larger peer-exchange buffer, but "
+                    f"{self._live_captures} captured search(es) still use the current one: "
+                    "release() them first, or capture the largest (Q, k) first")
             self._peer.close()
             self._peer = None
         errs = []
@@ -273,8 +295,12 @@ class ShardedGallery:
         if self.world > 1 and self._peer_exchange(num_queries, k) is None:
             raise RuntimeError("capture() needs the peer-memory exchange (exchange='peer'/'auto' on "
                                f"GPUs of one box); unavailable: {self.exchange_error}")
-        return CapturedSearch(lambda q, kk: self.search(q, kk), num_queries, emb.shape[1], k,
-                              emb.dtype, emb.device)
+        def released():
+            self._live_captures -= 1
+        cap = CapturedSearch(lambda q, kk: self.search(q, kk), num_queries, emb.shape[1], k,
+                             emb.dtype, emb.device, on_release=released)
+        self._live_captures += 1
+        return cap
 
     def search_lagged(self, queries: torch.Tensor, k: int) -> Optional[TopK]:
         """A stream of searches with one search of slack between the ranks.  Enqueues this

@@ -138,8 +138,25 @@ class GalleryWriter:
     def __enter__(self) -> "GalleryWriter":
         return self
 
-    def __exit__(self, *exc) -> None:
-        self.close()
+    def abort(self) -> None:
+        """Give up on a partially written gallery: the file is removed (its header was never
+        sealed — the magic is still zero — so even a copy taken now is rejected by the reader)."""
+        if self._closed:
+            return
+        self._f.close()
+        self._closed = True
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+    def __exit__(self, exc_type, exc, tb) -> None:
+        # an append that raised part-way leaves fewer rows than the caller meant to write: sealing
+        # that would hand later searches a gallery that silently misses rows
+        if exc_type is not None:
+            self.abort()
+        else:
+            self.close()
 
 
 class GalleryBuilder:

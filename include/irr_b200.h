@@ -103,18 +103,27 @@ IRR_API irr_status irr_cosine_topk(const void* q, const void* g, const float* g_
                                    int64_t* out_idx, void* workspace, size_t workspace_bytes,
                                    irr_stream_t stream);
 
-/* Test / bring-up aid: the dense score matrix the bf16 tensor-core path ranks, out [Q,N] fp32
- * (same kernel, epilogue writes scores instead of selecting).  Small N only. */
+/* ---- Measurement / test aids: NOT part of the stable ABI (no reference call site stands behind
+ * them; they exist for tests/, bench.py and scripts/ and may change between versions) ----------
+ *
+ * irr_cosine_scores_bf16: the dense score matrix the bf16 tensor-core path ranks, out [Q,N] fp32
+ * (same kernel, epilogue writes scores instead of selecting).  Small N only.
+ *
+ * irr_profile_next_topk (bench.py's roofline leg): arm a pair of caller-created cudaEvent_t; the
+ * NEXT irr_cosine_topk call made by this host thread records them on its stream immediately before
+ * and after the dominant top-k kernel (excluding any norm pre-pass and the partial-list merge),
+ * then disarms.  Pass NULLs to disarm.
+ *
+ * irr_debug_occupy_sms: launch `ctas` CTAs that each hold `smem_bytes` of shared memory and spin
+ * for `nanoseconds` (<= 2 s) on `stream` — a stand-in for a foreign kernel holding SMs, used by the
+ * test that the persistent kernels neither hang nor trap when the GPU is not theirs alone. */
 IRR_API irr_status irr_cosine_scores_bf16(const void* q, const void* g, int64_t Q, int64_t N,
                                           int32_t D, float eps, float* out_scores,
                                           void* workspace, size_t workspace_bytes,
                                           irr_stream_t stream);
-
-/* Measurement aid (bench.py's roofline leg): arm a pair of caller-created cudaEvent_t; the NEXT
- * irr_cosine_topk call made by this host thread records them on its stream immediately before and
- * after the dominant top-k kernel (excluding the norm pre-pass and the partial-list merge), then
- * disarms.  Pass NULLs to disarm. */
 IRR_API void irr_profile_next_topk(void* ev_start, void* ev_stop);
+IRR_API irr_status irr_debug_occupy_sms(int32_t ctas, int32_t smem_bytes, int64_t nanoseconds,
+                                        irr_stream_t stream);
 
 /* 1/max(|row|,eps) for every row of x [N,D] -> out fp32[N]; what a gallery handle caches. */
 IRR_API irr_status irr_row_inv_norms(const void* x, int64_t N, int32_t D, irr_dtype dt, float eps,

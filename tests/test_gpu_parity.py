@@ -332,6 +332,96 @@ def test_k10_bf16_d2560():
 
 
 # -------------------------------------------------------------------------------------------------
+# dispatch regimes of the bf16 tensor path: every kernel instantiation against the oracle
+# -------------------------------------------------------------------------------------------------
+def _check_sorted(res, s, ov, oi, k, tol):
+    """topk_matches against an oracle score matrix that is already stably sorted (ov, oi)."""
+    gv, gi = res.values.double().cpu(), res.indices.cpu()
+    assert ((gv - ov[:, :k]).abs().max().item()) <= tol
+    same = gi == oi[:, :k]
+    gap = (s.gather(1, gi.clamp_min(0)) - ov[:, :k]).abs()
+    bad = (~same) & ((gap > tol) | (gi < 0))
+    assert int(bad.sum()) == 0, (int(bad.sum()), float(gap[~same].max()))
+    assert (res.values[:, :-1] >= res.values[:, 1:]).all()
+
+
+REGIME_Q = (128, 129, 256, 257, 384, 385, 512, 513, 768, 1100)
+
+
+@pytest.mark.parametrize("D,N", [(64, 40_003), (1536, 12_011), (2560, 8_009)])
+@pytest.mark.parametrize("Q", REGIME_Q)
+def test_dispatch_regime_sweep(Q, D, N):
+    """Every instantiation bf16_cosine_topk can dispatch to (csrc/cosine_topk_bf16.cu), reached
+    through irr_cosine_topk with Q on both sides of each switch point, cached and uncached gallery
+    norms, k in {3, 10, 16} (KMAX = 4 / 16), ragged N (last tile and last chunk partial), on a
+    gallery with exact duplicate rows (ties -> lower index) — against the fp64 oracle of
+    train/train_efficient_cos_con_ce_loss.py:273-276 on the same bf16-valued inputs:
+      Q <= 128              launch<KM,false,FN,1>     FN = fused norm warps when uncached
+      129..256 cached       launch_pair<KM, cached>   one CTA pair streams the gallery once
+      129..256 uncached     launch_pair<KM, fused>    norms from the staged tiles (both CTAs)
+      257..384              launch<KM,false,false,1> cached / launch_pair<KM, fused> uncached
+      >= 385                launch_pair<KM, cached|fused>
+    """
+    q, gal = synthetic.tied_gallery(N, D, Q, seed=Q + D, dtype=torch.bfloat16)
+    s = ref.cos_scores(q, gal)
+    ov, oi = torch.sort(s, dim=1, descending=True, stable=True)
+    ov, oi = ov[:, :16], oi[:, :16]
+    qd, gd = q.cuda(), gal.cuda()
+    handle = irr.Gallery(gd)                                   # cached inverse norms
+    for k in (3, 10, 16):
+        unc = irr.cosine_topk(qd, gd, k)
+        _check_sorted(unc, s, ov, oi, k, 1e-4)
+        cac = handle.search(qd, k)
+        _check_sorted(cac, s, ov, oi, k, 1e-4)
+        # both norm sources rank identically; values differ by the norms' summation order only
+        assert torch.equal(cac.indices, unc.indices)
+        assert (cac.values - unc.values).abs().max() < 1e-6
+        # the duplicated best match: lower index first, bit-identical scores
+        assert (unc.indices[:, 0] < unc.indices[:, 1]).all()
+        assert (unc.values[:, 0] == unc.values[:, 1]).all()
+
+
+def test_config5_scaled_down_k10_q8192_d2560():
+    """BASELINE.json configs[4] (10M x 2560 bf16, Q=8192, k=10 over 8 GPUs) scaled to one eighth of
+    one GPU's shard: N = 160,000 rows, the same Q, k, D — the kernel instantiation the full config
+    runs (cosine_topk_bf16_pair_kernel<16, *>, 32 query-tile pairs).  Ten planted neighbours per
+    query (sigma 0.008..0.035) must come back in rank order; values against torch's
+    cosine_similarity on the returned rows and against the fp64 oracle for a sample of queries; the
+    one-device emulation of the 8 row shards + merge kernel must be bit-identical to the unsharded
+    search (reference semantics: torch.topk(sim, k), train_efficient_cos_con_ce_loss.py:276)."""
+    N, D, Q, k = 160_000, 2560, 8192, 10
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(4)
+    g = torch.randn(N, D, device=dev, dtype=torch.bfloat16, generator=gen)
+    base = torch.randn(Q, D, device=dev, generator=gen)
+    pos = torch.randperm(N, device=dev, generator=gen)[: Q * k].view(Q, k)
+    sig = torch.linspace(0.008, 0.035, k).tolist()
+    for j in range(k):
+        g[pos[:, j]] = (base + sig[j] * D ** 0.5 * torch.randn(Q, D, device=dev, generator=gen)).bfloat16()
+    q = (3.7 * base).bfloat16()
+    del base
+    for handle in (None, irr.Gallery(g)):                      # norms inside the kernel / cached
+        res = irr.cosine_topk(q, g, k) if handle is None else handle.search(q, k)
+        assert torch.equal(res.indices, pos)
+        want = torch.nn.functional.cosine_similarity(q.float().unsqueeze(1), g[res.indices].float(),
+                                                     dim=2, eps=1e-6)
+        assert (res.values - want).abs().max() < 1e-5
+        sel = torch.arange(0, Q, Q // 32, device=dev)
+        _, _, s = ref.cos_topk_stable(q[sel].cpu(), g.cpu(), k)
+        m = ref.topk_matches(res.values[sel], res.indices[sel], s, k, 1e-4, False)
+        assert m["val_err"] <= 1e-4 and m["bad_idx"] == 0, m
+    G = 8
+    cv, ci = [], []
+    for r in range(G):
+        lo, hi = irr.shard_bounds(N, G, r)
+        part = irr.cosine_topk(q, g[lo:hi], k, idx_offset=lo)
+        cv.append(part.values)
+        ci.append(part.indices)
+    mv, mi = _ops.topk_merge(torch.stack(cv), torch.stack(ci))
+    assert torch.equal(mi, res.indices) and (mv - res.values).abs().max() < 1e-6
+
+
+# -------------------------------------------------------------------------------------------------
 # full-size headline config: 1M x 1536 bf16, Q = 1 / 64 / 4096 — size-independent properties
 # -------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
@@ -631,6 +721,99 @@ def test_search_pipeline_overlapped_batches():
             assert torch.equal(i, want.indices.cpu()) and torch.equal(v, want.values.cpu())
     with pytest.raises(ValueError):
         list(irr.SearchPipeline(g.search, Q, D, k, torch.bfloat16, "cuda").run([batches[0][:5]]))
+
+
+def test_search_pipeline_over_a_captured_search():
+    """SearchPipeline driving a CapturedSearch: the graph's static outputs are overwritten by the
+    next replay, so the pipeline must order batch n's read-back before the replay for batch n+1.
+    A small gallery makes the search short enough for the race to bite if that order is missing."""
+    N, D, Q, k = 2_000, 64, 512, 3
+    _, gal = synthetic.iid_gallery(N, D, 1, seed=41, dtype=torch.bfloat16)
+    g = irr.Gallery(gal.cuda())
+    cap = g.capture(Q, k)
+    assert cap.static_outputs
+    batches = [synthetic.iid_gallery(4, D, Q, seed=50 + i, dtype=torch.bfloat16)[0].pin_memory()
+               for i in range(12)]
+    pipe = irr.SearchPipeline(cap, Q, D, k, torch.bfloat16, "cuda", depth=2)
+    assert pipe.static_outputs
+    for _ in range(3):
+        got = [(v.clone(), i.clone()) for v, i in pipe.run(iter(batches))]
+        assert len(got) == len(batches)
+        for (v, i), qb in zip(got, batches):
+            want = g.search(qb.cuda(), k)
+            assert torch.equal(i, want.indices.cpu()) and torch.equal(v, want.values.cpu())
+    with pytest.raises(ValueError, match="captured for k"):
+        cap(batches[0].cuda(), k + 1)
+
+
+def test_losses_first_called_inside_a_graph_capture():
+    """The loss kernels' self-resetting sync word must not live in a CUDA graph's private pool
+    beyond the capture: first use inside a capture, then eager calls and replays, all correct."""
+    from imageretrievalresearch_b200 import _ops as ops
+    q, p, n = [t.cuda() for t in synthetic.triplets(300, 256, seed=9)]
+    want = ref.four_losses(q.cpu(), p.cpu(), n.cpu(), 0.3)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        ops._zeroed.pop((0, st.cuda_stream), None)        # nothing cached for the capture stream
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            out = irr.triplet_losses_fwd_bwd(q, p, n, 0.3)
+        assert (0, st.cuda_stream) not in ops._zeroed         # pool memory was not cached
+        for _ in range(3):
+            g.replay()
+        st.synchronize()
+        assert ((out.losses.cpu() - want).abs() <= LOSS_REL * want.abs() + 1e-9).all()
+        junk = [torch.full((1 << 16,), 0xFF, dtype=torch.uint8, device="cuda") for _ in range(8)]
+        eager = irr.triplet_losses_fwd_bwd(q, p, n, 0.3)      # allocates its own, zeroed, cached
+        st.synchronize()
+        assert ((eager.losses.cpu() - want).abs() <= LOSS_REL * want.abs() + 1e-9).all()
+        del junk
+    torch.cuda.current_stream().wait_stream(st)
+
+
+@pytest.mark.parametrize("dtype,k", [(torch.bfloat16, 3), (torch.float32, 3), (torch.bfloat16, 40)])
+def test_empty_gallery_shard_is_all_padding(dtype, k):
+    """A shard with no rows (total rows < ranks): every slot is (-inf, -1), status OK."""
+    q = torch.randn(5, 64, device="cuda").to(dtype)
+    empty = torch.empty(0, 64, device="cuda", dtype=dtype)
+    res = irr.cosine_topk(q, empty, k, allow_short=True, idx_offset=77)
+    assert (res.indices == -1).all() and torch.isinf(res.values).all() and (res.values < 0).all()
+    g = irr.Gallery(empty)
+    r2 = g.search(q, k, allow_short=True)
+    assert (r2.indices == -1).all()
+    # merged with a real shard the padding disappears
+    _, gal = synthetic.iid_gallery(50, 64, 1, seed=3, dtype=dtype)
+    real = irr.cosine_topk(q, gal.cuda(), min(k, 16), allow_short=True)
+    pad = irr.cosine_topk(q, empty, min(k, 16), allow_short=True)
+    mv, mi = _ops.topk_merge(torch.stack([pad.values, real.values]), torch.stack([pad.indices, real.indices]))
+    assert torch.equal(mi, real.indices) and torch.equal(mv, real.values)
+
+
+@pytest.mark.parametrize("Q,cached", [(640, False), (4096, False), (300, False), (640, True)])
+def test_search_completes_while_a_foreign_kernel_holds_sms(Q, cached):
+    """The persistent kernels must neither hang nor trap when the GPU is not theirs alone (a DDP
+    step's NCCL kernels, MPS neighbours): 40 SMs are held by a spinning kernel with 200 KB of shared
+    memory each on another stream for 150 ms while the search is issued.  The variant whose
+    epilogues wait for norm producers in OTHER CTAs (Q >= 513 uncached) is launched cooperatively:
+    the driver co-schedules the whole grid once it fits instead of letting resident CTAs spin on
+    CTAs that cannot start (4 s watchdog -> trap before this was fixed)."""
+    lib = _lib.load()
+    N, D, k = 60_000, 256, 3
+    q, gal, pos = synthetic.planted_gallery(N, D, Q, k, seed=Q, dtype=torch.bfloat16)
+    qd, gd = q.cuda(), gal.cuda()
+    handle = irr.Gallery(gd) if cached else None
+    run = (lambda: handle.search(qd, k)) if cached else (lambda: irr.cosine_topk(qd, gd, k))
+    want = run()
+    assert torch.equal(want.indices.cpu(), pos)
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    st = lib.irr_debug_occupy_sms(40, 200 * 1024, 150_000_000, side.cuda_stream)
+    assert st == 0
+    outs = [run() for _ in range(3)]
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o.indices, want.indices) and torch.equal(o.values, want.values)
 
 
 def test_sharded_c_entry_single_rank():

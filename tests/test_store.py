@@ -59,6 +59,28 @@ def test_rejects_foreign_truncated_and_misaligned(tmp_path):
     assert irr.GalleryStore(tmp_path / "y.irrg").rows == 0
 
 
+def test_writer_that_fails_midway_leaves_no_gallery(tmp_path):
+    """An append that raises inside the `with` block must not seal a short file: the reader would
+    accept it and later searches would silently miss rows."""
+    p = tmp_path / "partial.irrg"
+    with pytest.raises(ValueError, match="expected"):
+        with irr.GalleryWriter(p, 64, torch.float32) as w:
+            w.append(torch.randn(10, 64))
+            w.append(torch.randn(10, 32))             # wrong width: raises part-way through
+    assert not p.exists()
+    # the same bytes sealed by nobody are rejected, too (magic still zero)
+    w = irr.GalleryWriter(p, 64, torch.float32)
+    w.append(torch.randn(10, 64))
+    w._f.flush()
+    with pytest.raises(ValueError, match="magic"):
+        irr.GalleryStore(p)
+    w.abort()
+    assert not p.exists()
+    w.abort()                                          # idempotent
+    with pytest.raises(RuntimeError, match="closed"):
+        w.append(torch.randn(1, 64))
+
+
 def test_block_ranges():
     assert irr.block_ranges(10, 4) == [(0, 4), (4, 8), (8, 10)]
     assert irr.block_ranges(0, 4) == []
