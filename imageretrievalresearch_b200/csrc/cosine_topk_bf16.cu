@@ -52,6 +52,13 @@ struct Plan {
   int m_tiles, n_tiles, tiles_per_chunk, n_chunks, grid;
 };
 
+// The two tensor maps of a query batch (see encode_queries)
+struct QueryMaps {
+  CUtensorMap full, tail;
+  int tail_tile;    // index of the ragged tile, -1 if Q is a multiple of 128
+  int tail_bytes;   // bytes one k-block of the ragged tile brings in
+};
+
 // Measurement knobs for profiles/ (environment, read ONCE per process) — not an API.
 struct Knobs {
   int tiles_per_chunk;       // IRR_TILES_PER_CHUNK: override the planner's chunk length
@@ -127,20 +134,33 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
   return (j & 16) ? d[1] : d[0];
 }
 
-// three-input maximum (one FMNMX3 on sm_100)
+// three-input maximum that propagates NaN (one FMNMX3.NAN on sm_100): a NaN score is the LARGEST
+// in torch.topk's order, so the group maximum must not hide it
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-// largest of 32 register values in 17 instructions
+__device__ __forceinline__ float max2(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+// largest of 32 register values (NaN if any is NaN) in 17 instructions
 __device__ __forceinline__ float max32(const float (&v)[32]) {
   float a[11];
 #pragma unroll
   for (int i = 0; i < 10; ++i) a[i] = max3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-  a[10] = fmaxf(v[30], v[31]);
+  a[10] = max2(v[30], v[31]);
   const float b0 = max3(a[0], a[1], a[2]), b1 = max3(a[3], a[4], a[5]), b2 = max3(a[6], a[7], a[8]);
-  return fmaxf(max3(b0, b1, b2), fmaxf(a[9], a[10]));
+  return max2(max3(b0, b1, b2), max2(a[9], a[10]));
+}
+// "score s still enters a list whose k-th best is kth, given the shared floor": kth must be a
+// number (a list full of NaNs is closed: later columns have higher indices), s larger than kth or
+// NaN, and not strictly below the floor.  Written with unordered compares: no extra instructions
+// for the NaN rule on the hot path.
+__device__ __forceinline__ bool wants(float s, float kth, float floor) {
+  return kth == kth && !(s <= kth) && !(s < floor);
 }
 
 // `floor` is a lower bound on this row's final k-th best score published by other gallery chunks
@@ -182,13 +202,13 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, i
       // instructions of the per-column masks (a column qualifies iff the row's maximum does).
       const float kth = top.v[KMAX - 1];
       const float vmax = max32(v);
-      if (!__any_sync(0xffffffffu, vmax > kth && vmax >= floor)) continue;
+      if (!__any_sync(0xffffffffu, wants(vmax, kth, floor))) continue;
       // Which columns?  Every lane builds its own 32-bit take-mask with independent compares (no
       // per-column vote/branch latency chain — there is a single epilogue warp per scheduler), one
       // REDUX ORs the masks, and the insert code runs only for the set bits.
       uint32_t mine = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mine |= ((v[j] > kth && v[j] >= floor) ? 1u : 0u) << j;
+      for (int j = 0; j < 32; ++j) mine |= (wants(v[j], kth, floor) ? 1u : 0u) << j;
       const uint32_t any = __reduce_or_sync(0xffffffffu, mine);
       // ONE copy of the insert code (it is ~120 instructions for KMAX=16; unrolled per column it
       // would not fit the instruction cache): walk the set bits, fetching column j's score from
@@ -200,7 +220,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, i
         todo &= todo - 1;
         const float sj = pick32(v, j);
         // re-evaluated: an insert earlier in this group may have raised this row's threshold
-        const bool take = sj > top.v[KMAX - 1] && sj >= floor;
+        const bool take = wants(sj, top.v[KMAX - 1], floor);
         top.insert_ranked(take, sj, n0 + c + j);
       }
     }
@@ -271,13 +291,14 @@ struct SC {
 template <int KMAX, bool WRITE_SCORES, bool FUSE_NORM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                        const __grid_constant__ CUtensorMap tmap_q_tail,
                         const __grid_constant__ CUtensorMap tmap_g,
                         const float* __restrict__ g_inv_norm, const float* __restrict__ q_inv_norm,
                         int Q, int N, int num_kb, int k, int m_tiles, int n_tiles,
                         int tiles_per_chunk, int n_chunks, float* __restrict__ part_val,
                         int32_t* __restrict__ part_idx, float* __restrict__ scores_out,
-                        uint64_t g_policy, float eps, int a_rows, uint32_t* __restrict__ row_floor,
-                        int is_f16) {
+                        uint64_t g_policy, float eps, int tail_tile, int tail_bytes,
+                        uint32_t* __restrict__ row_floor, int is_f16) {
   using G = SC;
   constexpr int STAGES = G::STAGES;
   constexpr int ACC = G::ACC;
@@ -302,6 +323,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_q_tail);
     tma_prefetch_desc(&tmap_g);
   }
   if (warp == 1 && lane == 0) {
@@ -319,16 +341,10 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
-  if (a_rows < BLOCK_M) {
-    // small query batch: the TMA box only covers the first a_rows rows of each A stage; the MMA
-    // still reads 128 rows, so the rest is zeroed once here (their accumulator rows are ignored)
-    for (int s = 0; s < STAGES; ++s) {
-      uint4* a = reinterpret_cast<uint4*>(smem_gen + s * STAGE_BYTES);
-      for (int i = threadIdx.x; i < G::A_BYTES / 16; i += NUM_THREADS)
-        a[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    fence_proxy_async_smem();  // generic-proxy zeros ordered before the async-proxy (TMA) writes
-  }
+  // The last query tile may be ragged (Q % 128 rows): it is loaded through a tensor map whose box
+  // only covers the rows that exist, rounded up to the 8-row swizzle atom — out-of-bounds rows
+  // cost TMA time (Q=1 used to run slower than Q=64).  The MMA still reads 128 rows; whatever the
+  // rest of the A stage holds only reaches accumulator rows >= Q, which nobody reads.
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -350,9 +366,10 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (lane == 0) {
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
             const uint32_t b_dst = a_dst + G::A_BYTES;
-            mbar_arrive_expect_tx(full_bar(stage), a_rows * (BLOCK_K * 2) + B_STAGE_BYTES);
-            tma_load_2d(a_dst, &tmap_q, kb * BLOCK_K, mt * BLOCK_M, full_bar(stage),
-                        kPolicyEvictLast);
+            const bool tail = mt == tail_tile;
+            mbar_arrive_expect_tx(full_bar(stage), (tail ? tail_bytes : G::A_BYTES) + B_STAGE_BYTES);
+            tma_load_2d(a_dst, tail ? &tmap_q_tail : &tmap_q, kb * BLOCK_K, mt * BLOCK_M,
+                        full_bar(stage), kPolicyEvictLast);
             tma_load_2d(b_dst, &tmap_g, kb * BLOCK_K, t * BLOCK_N, full_bar(stage), g_policy);
           }
           __syncwarp();
@@ -451,6 +468,9 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
       const int row = mt * BLOCK_M + row_in_tile;
       top.reset();
+      // rows past the last query hold whatever the A stage held: their list starts closed (a NaN
+      // k-th entry admits nothing), so they never drag their warp into the insert path
+      if (row >= Q) top.v[KMAX - 1] = __uint_as_float(0x7fffffffu);
       float qn = 1.0f;
       if (WRITE_SCORES && row < Q) qn = q_inv_norm[row];
       for (int t = t0; t < t1; ++t, ++it) {
@@ -667,6 +687,7 @@ __device__ __forceinline__ void norm_row_sums(const uint4* r, int nt, float& sa,
 template <int KMAX, int NORMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NORMS != NORMS_CACHED ? P_THREADS_NORM : P_THREADS, 1)
 cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                             const __grid_constant__ CUtensorMap tmap_q_tail,
                              const __grid_constant__ CUtensorMap tmap_g,
                              const float* __restrict__ g_inv_norm, int Q, int N, int num_kb, int k,
                              int m_pairs, int n_tiles, int tiles_per_chunk, int n_chunks,
@@ -674,7 +695,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                              uint32_t* __restrict__ row_floor, int is_f16,
                              const uint4* __restrict__ g_rows, int vec_per_row, float eps,
                              float* __restrict__ norm_out, uint32_t* __restrict__ tile_rows_done,
-                             int norm_ahead) {
+                             int norm_ahead, int tail_tile, int tail_bytes) {
   constexpr bool NORMS_INSIDE = NORMS == NORMS_PRODUCERS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -705,6 +726,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_q_tail);
     tma_prefetch_desc(&tmap_g);
   }
   if (warp == 1 && lane == 0) {
@@ -732,11 +754,20 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
+    // bytes a query tile contributes to a stage: a whole tile, the ragged last tile's box (rows
+    // that exist, rounded up to the swizzle atom), or nothing for a tile past the last query — an
+    // odd number of query tiles leaves the last pair's second CTA without rows: no load at all,
+    // its MMA half multiplies whatever the stage holds into accumulator rows nobody reads
+    auto a_bytes = [&](int tile) {
+      return tile * BLOCK_M >= Q ? 0 : (tile == tail_tile ? tail_bytes : P_A_BYTES);
+    };
     for (int u = cluster_id; u < total_units; u += num_clusters) {
       const int chunk = u / m_pairs, mp = u - chunk * m_pairs;
       const int mt = mp * 2 + static_cast<int>(rank);
       const int t0 = chunk * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
+      const uint32_t stage_tx = a_bytes(mp * 2) + a_bytes(mp * 2 + 1) + 2 * P_B_BYTES;
+      const int my_a = a_bytes(mt);
       for (int t = t0; t < t1; ++t) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 1100 + stage);
@@ -746,8 +777,10 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint32_t a_dst = smem_base + stage * P_STAGE_BYTES;
             const uint32_t b_dst = a_dst + P_A_BYTES;
             const uint32_t lead_full = mapa_rank(full_bar(stage), 0);
-            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * P_STAGE_BYTES);
-            tma_load_2d_pair(a_dst, &tmap_q, kb * BLOCK_K, mt * BLOCK_M, lead_full, kPolicyEvictLast);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+            if (my_a)
+              tma_load_2d_pair(a_dst, mt == tail_tile ? &tmap_q_tail : &tmap_q, kb * BLOCK_K,
+                               mt * BLOCK_M, lead_full, kPolicyEvictLast);
             tma_load_2d_pair(b_dst, &tmap_g, kb * BLOCK_K, t * BLOCK_N + static_cast<int>(rank) * P_B_ROWS,
                              lead_full, kPolicyEvictNormal);
           }
@@ -892,6 +925,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
       const int row = mt * BLOCK_M + row_in_tile;
       top.reset();
+      if (row >= Q) top.v[KMAX - 1] = __uint_as_float(0x7fffffffu);   // closed list (see above)
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         const int n0 = t * BLOCK_N;
@@ -1025,7 +1059,8 @@ template <int KMAX, int NORMS>
 irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, int64_t Q,
                        int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
                        uint32_t* row_floor, bool f16, const void* g, float eps, uint32_t* tile_done,
-                       cudaStream_t st, bool* refused) {
+                       cudaStream_t st, bool* refused, const QueryMaps& qm) {
+  const CUtensorMap& tqt = qm.tail;
   auto kern = cosine_topk_bf16_pair_kernel<KMAX, NORMS>;
   static std::atomic<uint64_t> attr_done{0};
   if (attr_needed(attr_done)) {
@@ -1047,10 +1082,10 @@ irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float
     cfg.numAttrs = 1;
     profile_mark_start(st);
     const cudaError_t e = cudaLaunchKernelEx(
-        &cfg, kern, tq, tg, gin, static_cast<int>(Q), static_cast<int>(N), num_kb, static_cast<int>(k),
+        &cfg, kern, tq, tqt, tg, gin, static_cast<int>(Q), static_cast<int>(N), num_kb, static_cast<int>(k),
         p.m_tiles, p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi, row_floor, f16 ? 1 : 0,
         static_cast<const uint4*>(g), D * 2 / 16, eps, const_cast<float*>(gin), tile_done,
-        knobs().norm_ahead);
+        knobs().norm_ahead, qm.tail_tile, qm.tail_bytes);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources ||
         e == cudaErrorNotSupported) {
       cudaGetLastError();
@@ -1064,9 +1099,10 @@ irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float
   }
   profile_mark_start(st);
   kern<<<p.grid, threads, P_SMEM_ALLOC, st>>>(
-      tq, tg, gin, static_cast<int>(Q), static_cast<int>(N), num_kb, k, p.m_tiles, p.n_tiles,
+      tq, tqt, tg, gin, static_cast<int>(Q), static_cast<int>(N), num_kb, k, p.m_tiles, p.n_tiles,
       p.tiles_per_chunk, p.n_chunks, pv, pi, row_floor, f16 ? 1 : 0, static_cast<const uint4*>(g),
-      D * 2 / 16, eps, const_cast<float*>(gin), tile_done, knobs().norm_ahead);
+      D * 2 / 16, eps, const_cast<float*>(gin), tile_done, knobs().norm_ahead, qm.tail_tile,
+      qm.tail_bytes);
   profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -1129,14 +1165,22 @@ bool encode_bf16_rows(CUtensorMap* m, const void* base, int64_t rows, int64_t co
   return true;
 }
 
-// rows of the query TMA box: a whole 128-row tile, or for a single small batch just the rows
-// that exist (rounded up to the 8-row swizzle atom) — out-of-bounds rows cost TMA time
-int a_box_rows(int64_t Q) {
-  return Q >= BLOCK_M ? BLOCK_M : static_cast<int>((Q + 7) / 8 * 8);
+// The two tensor maps of a query batch: whole 128-row tiles, and the ragged last tile (Q % 128
+// rows) whose box only covers the rows that exist, rounded up to the 8-row swizzle atom —
+// out-of-bounds rows cost TMA time.
+bool encode_queries(QueryMaps* m, const void* q, int64_t Q, int64_t D, bool f16) {
+  const int rem = static_cast<int>(Q % BLOCK_M);
+  const int tail_rows = rem ? (rem + 7) / 8 * 8 : BLOCK_M;
+  m->tail_tile = rem ? static_cast<int>(Q / BLOCK_M) : -1;
+  m->tail_bytes = tail_rows * BLOCK_K * 2;
+  if (!encode_bf16_rows(&m->full, q, Q, D, BLOCK_M, f16)) return false;
+  if (rem) return encode_bf16_rows(&m->tail, q, Q, D, tail_rows, f16);
+  m->tail = m->full;
+  return true;
 }
 
 template <int KMAX, bool WS, bool FN>
-irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, const float* qin,
+irr_status launch(const QueryMaps& qm, const CUtensorMap& tg, const float* gin, const float* qin,
                   int64_t Q, int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
                   float* scores, float eps, uint32_t* row_floor, bool f16, cudaStream_t st) {
   auto kern = cosine_topk_bf16_kernel<KMAX, WS, FN>;
@@ -1151,11 +1195,11 @@ irr_status launch(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin
   // query tiles in L2; with several query tiles the gallery tiles are the L2-shared operand
   const uint64_t g_policy = p.m_tiles == 1 ? kPolicyEvictFirst : kPolicyEvictNormal;
   if (!WS) profile_mark_start(st);
-  kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(tq, tg, gin, qin, static_cast<int>(Q),
+  kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(qm.full, qm.tail, tg, gin, qin, static_cast<int>(Q),
                                                 static_cast<int>(N), num_kb, k, p.m_tiles,
                                                 p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
-                                                scores, g_policy, eps, a_box_rows(Q), row_floor,
-                                                f16 ? 1 : 0);
+                                                scores, g_policy, eps, qm.tail_tile, qm.tail_bytes,
+                                                row_floor, f16 ? 1 : 0);
   if (!WS) profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -1208,16 +1252,18 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
                               : static_cast<size_t>(Q) * 4,
       st));
 
-  CUtensorMap tq, tg;
-  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q), f16) ||
+  QueryMaps qm;
+  CUtensorMap tg;
+  if (!encode_queries(&qm, q, Q, D, f16) ||
       !encode_bf16_rows(&tg, g, N, D, pair ? P_B_ROWS : BLOCK_N, f16))
     return IRR_ERR_UNSUPPORTED_DEVICE;
+  const CUtensorMap& tq = qm.full;
   irr_status s = IRR_OK;
   if (pair) {
     const bool small_k = k <= 4;
     bool refused = false;
 #define IRR_LAUNCH_PAIR(KM, NM, GIN) \
-  s = launch_pair<KM, NM>(tq, tg, GIN, Q, N, D, k, p, pv, pi, row_floor, f16, g, eps, tile_done, st, &refused)
+  s = launch_pair<KM, NM>(tq, tg, GIN, Q, N, D, k, p, pv, pi, row_floor, f16, g, eps, tile_done, st, &refused, qm)
     if (mode == NORMS_PRODUCERS) {   // gin_ws is written by the kernel's own norm producers
       if (small_k) IRR_LAUNCH_PAIR(4, NORMS_PRODUCERS, gin_ws); else IRR_LAUNCH_PAIR(16, NORMS_PRODUCERS, gin_ws);
       if (s == IRR_OK && refused) mode = NORMS_CACHED;   // no co-resident grid: pre-pass instead
@@ -1245,7 +1291,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
       gin = gin_ws;
     }
 #define IRR_LAUNCH_SC(KM, FN)                                                                   \
-  s = launch<KM, false, FN>(tq, tg, FN ? nullptr : gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, \
+  s = launch<KM, false, FN>(qm, tg, FN ? nullptr : gin, nullptr, Q, N, D, k, p, pv, pi, nullptr, \
                             eps, row_floor, f16, st)
     if (fuse) { if (k <= 4) IRR_LAUNCH_SC(4, true); else IRR_LAUNCH_SC(16, true); }
     else      { if (k <= 4) IRR_LAUNCH_SC(4, false); else IRR_LAUNCH_SC(16, false); }
@@ -1269,10 +1315,11 @@ irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N
   s = row_inv_norms(q, Q, D, IRR_BF16, eps, qin, st);
   if (s != IRR_OK) return s;
   const Plan p = make_plan(Q, N);
-  CUtensorMap tq, tg;
-  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q)) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
+  QueryMaps qm;
+  CUtensorMap tg;
+  if (!encode_queries(&qm, q, Q, D, false) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N))
     return IRR_ERR_UNSUPPORTED_DEVICE;
-  return launch<4, true, false>(tq, tg, gin, qin, Q, N, D, 1, p, nullptr, nullptr, out_scores, eps,
+  return launch<4, true, false>(qm, tg, gin, qin, Q, N, D, 1, p, nullptr, nullptr, out_scores, eps,
                                 nullptr, false, st);
 }
 
@@ -1283,11 +1330,11 @@ irr_status bf16_scores_block(const void* q, const void* g, const float* g_inv_no
   if (device_cc() / 10 != 10) return IRR_ERR_UNSUPPORTED_DEVICE;
   const bool f16 = dt == IRR_F16;
   const Plan p = make_plan(Q, N);
-  CUtensorMap tq, tg;
-  if (!encode_bf16_rows(&tq, q, Q, D, a_box_rows(Q), f16) ||
-      !encode_bf16_rows(&tg, g, N, D, BLOCK_N, f16))
+  QueryMaps qm;
+  CUtensorMap tg;
+  if (!encode_queries(&qm, q, Q, D, f16) || !encode_bf16_rows(&tg, g, N, D, BLOCK_N, f16))
     return IRR_ERR_UNSUPPORTED_DEVICE;
-  return launch<4, true, false>(tq, tg, g_inv_norm, q_inv_norm, Q, N, D, 1, p, nullptr, nullptr,
+  return launch<4, true, false>(qm, tg, g_inv_norm, q_inv_norm, Q, N, D, 1, p, nullptr, nullptr,
                                 out_scores, eps, nullptr, f16, st);
 }
 

@@ -397,13 +397,22 @@ __device__ __forceinline__ uint32_t orderable(float v) {
   const uint32_t b = __float_as_uint(v);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+// the same map with every NaN on top (torch.topk's order: NaN is the largest value);
+// from_orderable(0xffffffff) is a NaN again
+__device__ __forceinline__ uint32_t orderable_nan_top(float v) {
+  return v != v ? 0xffffffffu : orderable(v);
+}
 __device__ __forceinline__ float from_orderable(uint32_t o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
 // ---- per-thread sorted top-k list in registers -----------------------------------------------
-// "better" = larger score, ties -> lower index (the rule irr_b200.h promises)
+// "better" = larger score, ties -> lower index (the rule irr_b200.h promises).  NaN scores (a
+// gallery or query row with a non-finite element: torch's cosine_similarity gives NaN there) order
+// the way torch.topk orders them: above every number; among themselves by the lower index.
 __device__ __forceinline__ bool cand_better(float va, long long ia, float vb, long long ib) {
+  const bool na = va != va, nb = vb != vb;
+  if (na || nb) return na && (!nb || ia < ib);
   return va > vb || (va == vb && ia < ib);
 }
 
@@ -418,14 +427,16 @@ struct TopKList {
       i[j] = static_cast<IdxT>(-1);
     }
   }
-  // candidates offered in increasing index order: strict '>' keeps the lower index first
+  // candidates offered in increasing index order: strict '>' keeps the lower index first.
+  // "a beats b" for a later candidate a: b is a number and a is larger or NaN — !(a <= b) is
+  // true for a NaN a, and a NaN b is never displaced
   __device__ __forceinline__ void push_ordered(float s, IdxT idx) {
-    if (s > v[KMAX - 1]) {
+    if (v[KMAX - 1] == v[KMAX - 1] && !(s <= v[KMAX - 1])) {
       v[KMAX - 1] = s;
       i[KMAX - 1] = idx;
 #pragma unroll
       for (int j = KMAX - 1; j > 0; --j) {
-        if (v[j] > v[j - 1]) {
+        if (v[j - 1] == v[j - 1] && !(v[j] <= v[j - 1])) {
           float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv;
           IdxT ti = i[j]; i[j] = i[j - 1]; i[j - 1] = ti;
         }
@@ -435,11 +446,12 @@ struct TopKList {
   // Same insert as push_ordered without a serial bubble chain: rank the candidate against all
   // entries at once (independent compares), then every slot picks {keep, take from above, take the
   // candidate} — high ILP, which matters with a single epilogue warp per scheduler.  `take` must
-  // imply s > v[KMAX-1]; lanes with take == false leave their list untouched.
+  // imply that s beats v[KMAX-1]; lanes with take == false leave their list untouched.
   __device__ __forceinline__ void insert_ranked(bool take, float s, IdxT idx) {
     int c = 0;  // entries that stay ahead of s: the earlier (lower) index wins ties
+    const bool s_nan = s != s;   // a NaN goes behind the NaNs already listed, ahead of every number
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j) c += (v[j] >= s) ? 1 : 0;
+    for (int j = 0; j < KMAX; ++j) c += (s_nan ? (v[j] != v[j]) : !(v[j] < s)) ? 1 : 0;
     if (!take) c = KMAX;
 #pragma unroll
     for (int j = KMAX - 1; j > 0; --j) {

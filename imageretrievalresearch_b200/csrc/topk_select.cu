@@ -24,7 +24,7 @@ constexpr int SEL_CHUNK = 2 * SEL_THREADS;    // columns scanned between flush c
 constexpr int SEL_FLUSH_AT = SEL_KEYS - SEL_BEST - SEL_CHUNK;  // 256: buffer can take one more chunk
 
 __device__ __forceinline__ unsigned long long make_key(float v, uint32_t idx) {
-  return (static_cast<unsigned long long>(orderable(v)) << 32) | (0xffffffffu - idx);
+  return (static_cast<unsigned long long>(orderable_nan_top(v)) << 32) | (0xffffffffu - idx);
 }
 
 // descending bitonic sort of SEL_KEYS keys by SEL_THREADS threads
@@ -62,8 +62,9 @@ topk_select_kernel(const float* __restrict__ scores, int64_t N, int k, int64_t i
       const int64_t c = base + h * SEL_THREADS + threadIdx.x;
       if (c < N) {
         const float v = __ldg(s + c);
-        // columns arrive in increasing index: a later column equal to the threshold loses the tie
-        if (!full ? (v == v) : (v > thr)) {
+        // columns arrive in increasing index: a later column equal to the threshold loses the tie;
+        // NaN is the largest score (torch.topk's order) and a NaN threshold closes the list
+        if (!full || (thr == thr && !(v <= thr))) {
           const int pos = atomicAdd(&count, 1);
           keys[SEL_BEST + pos] = make_key(v, static_cast<uint32_t>(c));
         }
@@ -95,7 +96,7 @@ constexpr int MRG_SLOTS = 2048;
 
 __device__ __forceinline__ bool before(float va, long long ia, float vb, long long ib) {
   if (ia < 0 || ib < 0) return ia >= 0 && ib < 0;   // real entries before padding
-  return va > vb || (va == vb && ia < ib);
+  return cand_better(va, ia, vb, ib);               // score desc (NaN on top), index asc
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)

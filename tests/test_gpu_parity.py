@@ -256,6 +256,63 @@ def test_zero_norm_rows_and_eps():
     assert (cs(gal[:8].cuda(), q.cuda()).cpu() - want).abs().max() < 1e-6
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Q,k", [(5, 3), (200, 3), (300, 10), (640, 10), (37, 40)])
+def test_non_finite_rows_rank_like_torch_topk(dtype, Q, k):
+    """NaN / Inf policy = torch's: a gallery row with a NaN or Inf element has cosine NaN with every
+    query (x / max(|x|, eps) is NaN there: train_efficient_cos_con_ce_loss.py:273), torch.topk
+    (:276) treats NaN as the LARGEST value, so such rows come back first — here lowest index first —
+    with value NaN, followed by the ordinary ranking; a query row with a non-finite element has NaN
+    scores everywhere.  Checked against torch's own cosine_similarity + topk on the CPU."""
+    N, D = 3000, 64
+    q, gal = synthetic.iid_gallery(N, D, Q, seed=Q + k)
+    q, gal = q.to(dtype), gal.to(dtype)
+    bad_rows = [17, 900, 2500]
+    gal[17, 5] = float("nan")
+    gal[900, 0] = float("inf")
+    gal[2500] = float("nan")
+    if Q > 4:
+        q[3, 1] = float("nan")
+        q[4, 7] = -float("inf")
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), k)
+    cached = irr.Gallery(gal.cuda()).search(q.cuda(), k)
+    cos = torch.nn.CosineSimilarity(dim=1, eps=1e-6)
+    good_g = torch.ones(N, dtype=torch.bool)
+    good_g[bad_rows] = False
+    for got in (res, cached):
+        gv, gi = got.values.cpu(), got.indices.cpu()
+        for i in range(Q):
+            sim = cos(q[i].float().unsqueeze(0), gal.float())
+            tv, ti = torch.topk(sim, k)
+            assert torch.equal(torch.isnan(gv[i]), torch.isnan(tv)), i      # as many NaNs, all first
+            if Q > 4 and i in (3, 4):
+                assert torch.isnan(gv[i]).all()
+                continue
+            nb = len(bad_rows)
+            assert gi[i, :nb].tolist() == bad_rows                           # lower index first
+            assert sorted(ti[:nb].tolist()) == bad_rows                      # torch returns the same rows
+            # the rest is the ordinary ranking of the finite rows
+            fin = sim.clone()
+            fin[~good_g] = -float("inf")
+            wv, wi = torch.sort(fin, descending=True, stable=True)
+            tol = FP32_REL if dtype == torch.float32 else 1e-4
+            assert (gv[i, nb:] - wv[: k - nb]).abs().max() <= tol
+            same = gi[i, nb:] == wi[: k - nb]
+            gap = (fin[gi[i, nb:]] - wv[: k - nb]).abs()
+            assert (same | (gap <= tol)).all()
+    # a row-sharded search (one-device emulation, merge kernel) agrees with the unsharded one
+    cv, ci = [], []
+    for r in range(4):
+        lo, hi = irr.shard_bounds(N, 4, r)
+        part = irr.cosine_topk(q.cuda(), gal[lo:hi].cuda(), k, idx_offset=lo)
+        cv.append(part.values)
+        ci.append(part.indices)
+    mv, mi = _ops.topk_merge(torch.stack(cv), torch.stack(ci))
+    assert torch.equal(mi, res.indices)
+    assert torch.equal(torch.isnan(mv), torch.isnan(res.values))
+    assert (torch.nan_to_num(mv) - torch.nan_to_num(res.values)).abs().max() < 1e-6
+
+
 def test_short_shard_and_errors():
     q, gal = synthetic.iid_gallery(2, 64, 4, seed=2)
     with pytest.raises(RuntimeError, match="out of range"):
