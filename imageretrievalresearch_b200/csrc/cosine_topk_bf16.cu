@@ -536,8 +536,9 @@ constexpr int P_A_BYTES = BLOCK_M * BLOCK_K * 2;               // 16 KB
 constexpr int P_B_BYTES = P_B_ROWS * BLOCK_K * 2;              // 16 KB
 constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;           // 32 KB
 constexpr int P_SMEM_TILES = P_STAGES * P_STAGE_BYTES;         // 196608
-// full / empty / norm-done per stage, accumulator full / empty / norms-published per accumulator stage
-constexpr int P_SMEM_BARS = (3 * P_STAGES + 3 * ACC_STAGES) * 8;
+// full / empty / norm-done / tile-landed per stage, accumulator full / empty / norms-published per
+// accumulator stage
+constexpr int P_SMEM_BARS = (4 * P_STAGES + 3 * ACC_STAGES) * 8;
 constexpr int P_SMEM_TOTAL = P_SMEM_TILES + SMEM_GN + P_SMEM_BARS + 16;
 constexpr int P_SMEM_ALLOC = P_SMEM_TOTAL + 1024;
 constexpr int P_THREADS = 256;
@@ -664,9 +665,12 @@ __device__ __forceinline__ void norm_row_sums(const uint4* r, int nt, float& sa,
 //
 // NORMS_FUSED (no cached norms, one or two query-tile pairs): L2-normalisation fused into the load.
 // Four extra warps per CTA square-sum the CTA's half of every gallery tile out of the SAME
-// shared-memory stages the MMAs read — after the stage's MMAs retired (they wait on the stage's
-// "empty" barrier, which tcgen05.commit multicasts to both CTAs) and before the TMA producer may
-// refill it (it also waits on the stage's "norm done" barrier) — and publish 1/max(|g|,eps) of
+// shared-memory stages the MMAs read, while the MMAs read them: the leader's norm warps wait on
+// the stage's "full" barrier like the MMA issuer; both CTAs' loads complete on that barrier, which
+// lives in the leader, so one leader lane forwards the event to the partner's "tile landed"
+// barrier (a remote arrive) for the partner's norm warps.  The TMA producer refills a stage once
+// its MMAs retired AND the CTA's norm warps are done with it ("norm done" barrier).  The norm
+// warps publish 1/max(|g|,eps) of
 // their 128 rows into BOTH CTAs' norm buffers (own shared memory + a DSMEM store to the partner),
 // arriving on both CTAs' "norms published" barrier.  The gallery crosses HBM once, nothing is
 // exchanged through global memory and no CTA waits for a CTA outside its own cluster.  With many
@@ -708,6 +712,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + ACC_STAGES + s); };
   auto gnfull_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + 2 * ACC_STAGES + s); };
   auto normdone_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + 3 * ACC_STAGES + s); };
+  auto landed_bar = [&](int s) { return bars + 8u * (3 * P_STAGES + 3 * ACC_STAGES + s); };
   const uint32_t tmem_slot = bars + P_SMEM_BARS;
   float* gn_smem = reinterpret_cast<float*>(smem_gen + P_SMEM_TILES);
   volatile uint32_t* tmem_slot_gen =
@@ -739,7 +744,10 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(tempty_bar(s), 2 * (EPI_THREADS / 32));  // 4 epilogue warps of each CTA (leader's copy)
       mbar_init(gnfull_bar(s), 2 * (NORM_THREADS / 32)); // NORMS_FUSED: 4 norm warps of each CTA
     }
-    for (int s = 0; s < P_STAGES; ++s) mbar_init(normdone_bar(s), NORM_THREADS / 32);
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(normdone_bar(s), NORM_THREADS / 32);
+      mbar_init(landed_bar(s), 1);   // NORMS_FUSED, non-leader CTA: the leader forwards "stage full"
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
@@ -842,7 +850,12 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (int t = t0; t < t1; ++t, ++it) {
         float sa = 0.f, sb = 0.f;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase, 1500 + stage);   // the stage's MMAs have retired
+          if (rank == 0) {
+            mbar_wait(full_bar(stage), phase, 1500 + stage);          // both CTAs' tiles have landed
+            if (warp == P_NORM_WARP0 && lane == 0) mbar_arrive_cluster(mapa_rank(landed_bar(stage), 1));
+          } else {
+            mbar_wait_cluster(landed_bar(stage), phase, 1550 + stage);
+          }
           const uint4* r = reinterpret_cast<const uint4*>(smem_gen + stage * P_STAGE_BYTES + P_A_BYTES + nt * 128);
           if (f16) norm_row_sums<true>(r, nt, sa, sb);
           else     norm_row_sums<false>(r, nt, sa, sb);
@@ -850,9 +863,11 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (lane == 0) mbar_arrive(normdone_bar(stage));   // the producer may refill the stage
           if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
         }
-        // gn[as] is free: this tile's MMAs only started after both epilogues drained the tile that
-        // used accumulator stage `as` (and its norms) before
+        // gn[as] (in BOTH CTAs) is free once both epilogues drained the tile that used accumulator
+        // stage `as` and its norms before: in this variant they arrive on both CTAs' copies of the
+        // "accumulator drained" barrier (the norm warps may be several short tiles ahead of the MMAs)
         const uint32_t as = it & 1u;
+        mbar_wait_cluster(tempty_bar(as), ((it >> 1) & 1u) ^ 1u, 1700 + as);
         const float inv = 1.0f / fmaxf(sqrtf(sa + sb), eps);
         float* mine = gn_smem + as * BLOCK_N + static_cast<int>(rank) * P_B_ROWS + nt;
         *mine = inv;
@@ -959,7 +974,10 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         publish_floor<KMAX>(row_floor, row, Q, top, floor);
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));
+        if (lane == 0) {
+          mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));
+          if (NORMS == NORMS_FUSED) mbar_arrive_cluster(mapa_rank(tempty_bar(as), 1));
+        }
       }
       if (row < Q) {
         const size_t o = (static_cast<size_t>(chunk) * Q + row) * k;

@@ -372,7 +372,7 @@ irr_status irr_triplet_loss_fwd_bwd(const void* q, const void* p, const void* n,
   if (ng != 0 && ng != 3) return IRR_ERR_INVALID_ARG;
   const void* ptrs[6] = {q, p, n, dq, dp, dn};
   for (const void* x : ptrs) {
-    irr_status s = check_rows(x, D, dt);
+    irr_status s = check_rows(x, D, dt, true);
     if (s != IRR_OK) return s;
   }
   if (row_stats && !aligned16(row_stats)) return IRR_ERR_ALIGNMENT;
@@ -396,7 +396,7 @@ irr_status irr_triplet_loss_bwd(const void* q, const void* p, const void* n,
     return IRR_ERR_INVALID_ARG;
   const void* ptrs[6] = {q, p, n, dq, dp, dn};
   for (const void* x : ptrs) {
-    irr_status s = check_rows(x, D, dt);
+    irr_status s = check_rows(x, D, dt, true);
     if (s != IRR_OK) return s;
   }
   if (!aligned16(row_stats)) return IRR_ERR_ALIGNMENT;
@@ -421,7 +421,7 @@ irr_status irr_pair_loss_fwd_bwd(const void* a_, const void* b_, const float* la
   if ((da != nullptr) != (db != nullptr)) return IRR_ERR_INVALID_ARG;
   const void* ptrs[4] = {a_, b_, da, db};
   for (const void* x : ptrs) {
-    irr_status s = check_rows(x, D, dt);
+    irr_status s = check_rows(x, D, dt, true);
     if (s != IRR_OK) return s;
   }
   if (row_stats && !aligned16(row_stats)) return IRR_ERR_ALIGNMENT;
@@ -447,7 +447,7 @@ irr_status irr_pair_loss_bwd(const void* a_, const void* b_, const float* label,
   if (kind != IRR_LOSS_CONTRASTIVE && kind != IRR_LOSS_COSINE_EMBEDDING) return IRR_ERR_INVALID_ARG;
   const void* ptrs[4] = {a_, b_, da, db};
   for (const void* x : ptrs) {
-    irr_status s = check_rows(x, D, dt);
+    irr_status s = check_rows(x, D, dt, true);
     if (s != IRR_OK) return s;
   }
   if (!aligned16(row_stats)) return IRR_ERR_ALIGNMENT;

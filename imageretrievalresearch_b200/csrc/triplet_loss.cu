@@ -42,36 +42,61 @@ struct Coef {
 
 // One 16-byte vector as packed fp32 pairs: the arithmetic below runs on Blackwell's packed
 // FFMA2 / FMUL2 (two fp32 lanes per instruction), which halves the issue slots of a kernel whose
-// limit next to HBM is instruction issue.
-template <bool BF16>
+// limit next to HBM is instruction issue.  KIND = irr_dtype of the rows (IRR_F32 / IRR_BF16 / IRR_F16).
+template <int KIND>
 struct Vec {
-  static constexpr int N = BF16 ? 8 : 4;   // elements per vector
-  static constexpr int H = N / 2;          // float2 pairs per vector
+  static constexpr int N = KIND == IRR_F32 ? 4 : 8;   // elements per vector
+  static constexpr int H = N / 2;                     // float2 pairs per vector
   __device__ static __forceinline__ void unpack(const uint4& u, float2 (&f)[H]) {
-    if constexpr (BF16) {
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) f[j] = make_float2(bf16lo(w[j]), bf16hi(w[j]));
-    } else {
+    if constexpr (KIND == IRR_F32) {
       f[0] = make_float2(__uint_as_float(u.x), __uint_as_float(u.y));
       f[1] = make_float2(__uint_as_float(u.z), __uint_as_float(u.w));
+    } else {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        f[j] = KIND == IRR_F16 ? f16x2(w[j]) : make_float2(bf16lo(w[j]), bf16hi(w[j]));
     }
   }
   __device__ static __forceinline__ uint4 pack(const float2 (&f)[H]) {
     uint4 u;
-    if constexpr (BF16) {
+    if constexpr (KIND == IRR_F32) {
+      u = make_uint4(__float_as_uint(f[0].x), __float_as_uint(f[0].y), __float_as_uint(f[1].x),
+                     __float_as_uint(f[1].y));
+    } else {
       uint32_t w[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(f[j].x, f[j].y);
-        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        if constexpr (KIND == IRR_F16) {
+          const __half2 h = __floats2half2_rn(f[j].x, f[j].y);
+          w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        } else {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(f[j].x, f[j].y);
+          w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
       }
       u = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-      u = make_uint4(__float_as_uint(f[0].x), __float_as_uint(f[0].y), __float_as_uint(f[1].x),
-                     __float_as_uint(f[1].y));
     }
     return u;
+  }
+  // b - a for the contrastive distance.  fp32 / bf16 rows: the fp32 difference of the (exactly
+  // widened) values.  fp16 rows: the reference runs this path under autocast (precision=16,
+  // train/train_efficient_cos_con_ce_loss.py:465), where `fm2 - fm1` (utils/contrastive_loss.py:56)
+  // is an fp16 subtraction — rounded to fp16 — and only the following pow / sum are widened to
+  // fp32: the same rounding is applied here (one HSUB2 on the raw words), so the loss is the
+  // reference's value, not a more exact one.
+  __device__ static __forceinline__ void diff(const uint4& ua, const uint4& ub, const float2 (&fa)[H],
+                                              const float2 (&fb)[H], float2 (&d)[H]) {
+    if constexpr (KIND == IRR_F16) {
+      const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        d[j] = __half22float2(__hsub2(*reinterpret_cast<const __half2*>(&wb[j]),
+                                      *reinterpret_cast<const __half2*>(&wa[j])));
+    } else {
+#pragma unroll
+      for (int j = 0; j < H; ++j) d[j] = __ffma2_rn(fa[j], make_float2(-1.0f, -1.0f), fb[j]);  // exact like a subtraction
+    }
   }
 };
 
@@ -183,7 +208,7 @@ struct KParams {
   int stages;       // ring depth per group (1..MAX_STAGES)
 };
 
-template <bool BF16, bool TRIPLET, int GW>
+template <int KIND, bool TRIPLET, int GW>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 loss_fwd_bwd_kernel(const KParams P) {
   constexpr int GT = GW * 32;
@@ -208,6 +233,10 @@ loss_fwd_bwd_kernel(const KParams P) {
     fence_mbar_init();
   }
   __syncthreads();
+  // Programmatic dependent launch: everything above overlapped the tail of the previous kernel in
+  // the stream; nothing below (the first global read included) runs before that kernel has
+  // completed and flushed.  A no-op when the launch does not carry the attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // Row -> group map: row r belongs to group (r mod tg), numbered group-slot-major ACROSS the CTAs,
   // so that the rows left over after the last full round (B mod tg of them) go one or two to every
@@ -240,8 +269,7 @@ loss_fwd_bwd_kernel(const KParams P) {
   }
 
   float lsum[4] = {0.f, 0.f, 0.f, 0.f};   // kept by the group's first warp only
-  constexpr int VH = Vec<BF16>::H;
-  const float2 neg1 = splat2(-1.0f);
+  constexpr int VH = Vec<KIND>::H;
   int it = 0, s = 0;
   uint32_t parity = 0;
   for (int64_t row = gg; row < P.B; row += tg, ++it) {
@@ -254,22 +282,26 @@ loss_fwd_bwd_kernel(const KParams P) {
     // then the warp (warp_reduce8), then the group's warps (every warp, same fixed order) ----
     float2 aqq = splat2(0.f), app = aqq, ann = aqq, aqp = aqq, aqn = aqq, adp = aqq, adn = aqq;
     for (int v = gt; v < P.vec_per_row; v += GT) {
-      float2 fq[VH], fp[VH], fn[VH];
-      Vec<BF16>::unpack(sq[v], fq);
-      Vec<BF16>::unpack(sp[v], fp);
-      if (TRIPLET) Vec<BF16>::unpack(sn[v], fn);
+      float2 fq[VH], fp[VH], fn[VH], d[VH], e[VH];
+      const uint4 uq = sq[v], up = sp[v];
+      Vec<KIND>::unpack(uq, fq);
+      Vec<KIND>::unpack(up, fp);
+      Vec<KIND>::diff(uq, up, fq, fp, d);          // p - q
+      if (TRIPLET) {
+        const uint4 un = sn[v];
+        Vec<KIND>::unpack(un, fn);
+        Vec<KIND>::diff(uq, un, fq, fn, e);        // n - q
+      }
 #pragma unroll
       for (int j = 0; j < VH; ++j) {
         aqq = __ffma2_rn(fq[j], fq[j], aqq);
         app = __ffma2_rn(fp[j], fp[j], app);
         aqp = __ffma2_rn(fq[j], fp[j], aqp);
-        const float2 d = __ffma2_rn(fq[j], neg1, fp[j]);   // p - q, exact like a subtraction
-        adp = __ffma2_rn(d, d, adp);
+        adp = __ffma2_rn(d[j], d[j], adp);
         if (TRIPLET) {
           ann = __ffma2_rn(fn[j], fn[j], ann);
           aqn = __ffma2_rn(fq[j], fn[j], aqn);
-          const float2 e = __ffma2_rn(fq[j], neg1, fn[j]);
-          adn = __ffma2_rn(e, e, adn);
+          adn = __ffma2_rn(e[j], e[j], adn);
         }
       }
     }
@@ -333,9 +365,9 @@ loss_fwd_bwd_kernel(const KParams P) {
       uint4* gn = TRIPLET ? P.dn + row * P.vec_per_row : nullptr;
       for (int v = gt; v < P.vec_per_row; v += GT) {
         float2 fq[VH], fp[VH], fn[VH], oq[VH], op[VH], on[VH];
-        Vec<BF16>::unpack(sq[v], fq);
-        Vec<BF16>::unpack(sp[v], fp);
-        if (TRIPLET) Vec<BF16>::unpack(sn[v], fn);
+        Vec<KIND>::unpack(sq[v], fq);
+        Vec<KIND>::unpack(sp[v], fp);
+        if (TRIPLET) Vec<KIND>::unpack(sn[v], fn);
 #pragma unroll
         for (int j = 0; j < VH; ++j) {
           float2 a = __ffma2_rn(kqq, fq[j], __fmul2_rn(kqp, fp[j]));
@@ -347,18 +379,22 @@ loss_fwd_bwd_kernel(const KParams P) {
           oq[j] = a;
         }
         if (P.hints & 2) {
-          __stcs(gq + v, Vec<BF16>::pack(oq));
-          __stcs(gp + v, Vec<BF16>::pack(op));
-          if (TRIPLET) __stcs(gn + v, Vec<BF16>::pack(on));
+          __stcs(gq + v, Vec<KIND>::pack(oq));
+          __stcs(gp + v, Vec<KIND>::pack(op));
+          if (TRIPLET) __stcs(gn + v, Vec<KIND>::pack(on));
         } else {
-          gq[v] = Vec<BF16>::pack(oq);
-          gp[v] = Vec<BF16>::pack(op);
-          if (TRIPLET) gn[v] = Vec<BF16>::pack(on);
+          gq[v] = Vec<KIND>::pack(oq);
+          gp[v] = Vec<KIND>::pack(op);
+          if (TRIPLET) gn[v] = Vec<KIND>::pack(on);
         }
       }
     }
     if (++s == stages) { s = 0; parity ^= 1u; }
   }
+
+  // the next kernel in the stream may start its prologue now (it waits for this grid to complete
+  // before it touches memory, see above)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // ---- deterministic reduction of the loss scalars: one partial per group (fixed row -> group
   // map), the last CTA to check in adds them in a fixed order ----
@@ -411,13 +447,13 @@ struct BParams {
   uint4 *dq, *dp, *dn;
 };
 
-template <bool BF16, bool TRIPLET>
+template <int KIND, bool TRIPLET>
 __global__ void __launch_bounds__(256)
 loss_bwd_kernel(const BParams P) {
   const int lane = threadIdx.x & 31;
   const int64_t gw = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t tw = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-  constexpr int VH = Vec<BF16>::H;
+  constexpr int VH = Vec<KIND>::H;
   float w[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) w[j] = (TRIPLET || j == 0) ? __ldg(P.grad_out + j) * P.red_scale : 0.f;
@@ -442,9 +478,9 @@ loss_bwd_kernel(const BParams P) {
                  knn = splat2(c.ann);
     for (int v = lane; v < P.vec_per_row; v += 32) {
       float2 fq[VH], fp[VH], fn[VH], oq[VH], op[VH], on[VH];
-      Vec<BF16>::unpack(ldg_stream(sq + v), fq);
-      Vec<BF16>::unpack(ldg_stream(sp + v), fp);
-      if (TRIPLET) Vec<BF16>::unpack(ldg_stream(sn + v), fn);
+      Vec<KIND>::unpack(ldg_stream(sq + v), fq);
+      Vec<KIND>::unpack(ldg_stream(sp + v), fp);
+      if (TRIPLET) Vec<KIND>::unpack(ldg_stream(sn + v), fn);
 #pragma unroll
       for (int j = 0; j < VH; ++j) {
         float2 a = __ffma2_rn(kqq, fq[j], __fmul2_rn(kqp, fp[j]));
@@ -455,9 +491,9 @@ loss_bwd_kernel(const BParams P) {
         }
         oq[j] = a;
       }
-      gq[v] = Vec<BF16>::pack(oq);
-      gp[v] = Vec<BF16>::pack(op);
-      if (TRIPLET) gn[v] = Vec<BF16>::pack(on);
+      gq[v] = Vec<KIND>::pack(oq);
+      gp[v] = Vec<KIND>::pack(op);
+      if (TRIPLET) gn[v] = Vec<KIND>::pack(on);
     }
   }
 }
@@ -469,7 +505,7 @@ struct LaunchShape {
 
 // measurement knobs for profiles/ (environment, read once): IRR_LOSS_GW, IRR_LOSS_STAGES,
 // IRR_LOSS_HINTS — not an API
-struct LossKnobs { int gw, stages, hints; };
+struct LossKnobs { int gw, stages, hints, pdl; };
 const LossKnobs& loss_knobs() {
   static const LossKnobs k = []() {
     auto num = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
@@ -477,6 +513,7 @@ const LossKnobs& loss_knobs() {
     r.gw = num("IRR_LOSS_GW", 0);
     r.stages = num("IRR_LOSS_STAGES", 0);
     r.hints = num("IRR_LOSS_HINTS", 1);   // evict-first loads measured +3 % (profiles/r01_notes.md)
+    r.pdl = num("IRR_LOSS_PDL", 1);       // programmatic dependent launch (prologue overlaps the predecessor's tail)
     return r;
   }();
   return k;
@@ -567,7 +604,17 @@ irr_status loss_fwd_bwd(const LossArgs& a, void* ws, size_t ws_bytes, cudaStream
                                         SMEM_BUDGET));                                            \
       if (dev >= 0 && dev < 64) attr_done.fetch_or(1ull << dev, std::memory_order_relaxed);       \
     }                                                                                             \
-    kern<<<sh.grid, sh.groups * (GWV) * 32, sh.smem, st>>>(P);                                    \
+    cudaLaunchConfig_t cfg = {};                                                                  \
+    cfg.gridDim = dim3(sh.grid);                                                                  \
+    cfg.blockDim = dim3(sh.groups * (GWV) * 32);                                                  \
+    cfg.dynamicSmemBytes = sh.smem;                                                               \
+    cfg.stream = st;                                                                              \
+    cudaLaunchAttribute at[1];                                                                    \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                \
+    at[0].val.programmaticStreamSerializationAllowed = 1;                                         \
+    cfg.attrs = at;                                                                               \
+    cfg.numAttrs = loss_knobs().pdl ? 1 : 0;                                                      \
+    IRR_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));                                              \
   } while (0)
 #define IRR_LAUNCH_LOSS_GW(BF, TR)                                                                \
   do {                                                                                            \
@@ -576,9 +623,11 @@ irr_status loss_fwd_bwd(const LossArgs& a, void* ws, size_t ws_bytes, cudaStream
     else IRR_LAUNCH_LOSS(BF, TR, 1);                                                              \
   } while (0)
   if (a.dt == IRR_BF16) {
-    if (triplet) IRR_LAUNCH_LOSS_GW(true, true); else IRR_LAUNCH_LOSS_GW(true, false);
+    if (triplet) IRR_LAUNCH_LOSS_GW(IRR_BF16, true); else IRR_LAUNCH_LOSS_GW(IRR_BF16, false);
+  } else if (a.dt == IRR_F16) {
+    if (triplet) IRR_LAUNCH_LOSS_GW(IRR_F16, true); else IRR_LAUNCH_LOSS_GW(IRR_F16, false);
   } else {
-    if (triplet) IRR_LAUNCH_LOSS_GW(false, true); else IRR_LAUNCH_LOSS_GW(false, false);
+    if (triplet) IRR_LAUNCH_LOSS_GW(IRR_F32, true); else IRR_LAUNCH_LOSS_GW(IRR_F32, false);
   }
 #undef IRR_LAUNCH_LOSS_GW
 #undef IRR_LAUNCH_LOSS
@@ -609,11 +658,14 @@ irr_status loss_bwd(const LossArgs& a, const float* grad_out, cudaStream_t st) {
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   if (a.dt == IRR_BF16) {
-    if (triplet) loss_bwd_kernel<true, true><<<grid, 256, 0, st>>>(P);
-    else loss_bwd_kernel<true, false><<<grid, 256, 0, st>>>(P);
+    if (triplet) loss_bwd_kernel<IRR_BF16, true><<<grid, 256, 0, st>>>(P);
+    else loss_bwd_kernel<IRR_BF16, false><<<grid, 256, 0, st>>>(P);
+  } else if (a.dt == IRR_F16) {
+    if (triplet) loss_bwd_kernel<IRR_F16, true><<<grid, 256, 0, st>>>(P);
+    else loss_bwd_kernel<IRR_F16, false><<<grid, 256, 0, st>>>(P);
   } else {
-    if (triplet) loss_bwd_kernel<false, true><<<grid, 256, 0, st>>>(P);
-    else loss_bwd_kernel<false, false><<<grid, 256, 0, st>>>(P);
+    if (triplet) loss_bwd_kernel<IRR_F32, true><<<grid, 256, 0, st>>>(P);
+    else loss_bwd_kernel<IRR_F32, false><<<grid, 256, 0, st>>>(P);
   }
   IRR_LAUNCH_CHECK();
   return IRR_OK;

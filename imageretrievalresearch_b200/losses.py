@@ -35,11 +35,24 @@ def _label_tensor(label: Label, B: int, device: torch.device, what: str) -> torc
     return t
 
 
+def _autocast_rows(tensors, names, autocast_exact: bool):
+    """Rows for the loss kernels.  fp16 embeddings (what ``precision=16`` training produces,
+    train/train_efficient_cos_con_ce_loss.py:465) stay fp16 when EVERY operand is fp16 and
+    ``autocast_exact`` is set: the kernel then evaluates ``fm2 - fm1`` as the fp16 subtraction the
+    reference's autocast performs (utils/contrastive_loss.py:56; everything after it in fp32) and
+    emits fp16 gradients — the reference's numbers, not more exact ones.  Mixed fp16 / fp32 operands
+    promote to fp32 in the reference, too, and are widened here (as is everything when
+    ``autocast_exact=False``)."""
+    keep = autocast_exact and all(t.dtype == torch.float16 for t in tensors)
+    return [_ops.as_rows(t, n, keep_f16=keep) for t, n in zip(tensors, names)]
+
+
 class _PairLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b, label_t, kind, margin, mean):
+    def forward(ctx, a, b, label_t, kind, margin, mean, autocast_exact=True):
         lib = _lib.load()
-        ar, br = _ops.as_rows(a, "input1"), _ops.as_rows(b, "input2")
+        ar, br = _autocast_rows((a, b), ("input1", "input2"), autocast_exact)
+        ar, br = _ops.same_kind(ar, br)
         _ops.check_same(ar, br, "input1", "input2")
         if ar.shape != br.shape:
             raise RuntimeError(f"shape mismatch: {tuple(ar.shape)} vs {tuple(br.shape)}")
@@ -75,7 +88,7 @@ class _PairLossFn(torch.autograd.Function):
                                         _ops.dtype_code(ar), kind, margin, mean, _ops.ptr(da),
                                         _ops.ptr(db), _ops.stream_ptr(dev)), "irr_pair_loss_bwd")
         return (da.to(a_dtype) if ctx.needs_input_grad[0] else None,
-                db.to(b_dtype) if ctx.needs_input_grad[1] else None, None, None, None, None)
+                db.to(b_dtype) if ctx.needs_input_grad[1] else None, None, None, None, None, None)
 
 
 class ContrastiveLoss(torch.nn.Module):
@@ -84,15 +97,17 @@ class ContrastiveLoss(torch.nn.Module):
     with ``d = sum((fm2-fm1)^2, dim=1)``, reduced by mean (default) or sum.  One fused kernel per
     direction instead of ~12 elementwise launches; differentiable w.r.t. fm1 and fm2."""
 
-    def __init__(self, margin: float) -> None:
+    def __init__(self, margin: float, autocast_exact: bool = True) -> None:
         super().__init__()
         self.margin, self.eps = margin, 1e-9
+        self.autocast_exact = autocast_exact   # fp16 inputs: reproduce autocast's fp16 `fm2 - fm1`
 
     def forward(self, fm1: torch.Tensor, fm2: torch.Tensor, label: Label, mean: bool = True
                 ) -> torch.Tensor:
         _ops._require_cuda(fm1, "fm1")
         lab = _label_tensor(label, fm1.shape[0], fm1.device, "label")
-        return _PairLossFn.apply(fm1, fm2, lab, IRR_LOSS_CONTRASTIVE, float(self.margin), bool(mean))
+        return _PairLossFn.apply(fm1, fm2, lab, IRR_LOSS_CONTRASTIVE, float(self.margin), bool(mean),
+                                 self.autocast_exact)
 
 
 class CosineEmbeddingLoss(torch.nn.Module):
@@ -133,8 +148,10 @@ class TripletLosses(NamedTuple):
         return self.con_pos + self.con_neg
 
 
-def _triplet_rows(q, p, n):
-    qr, pr, nr = _ops.as_rows(q, "qry"), _ops.as_rows(p, "pos"), _ops.as_rows(n, "neg")
+def _triplet_rows(q, p, n, autocast_exact: bool = True):
+    qr, pr, nr = _autocast_rows((q, p, n), ("qry", "pos", "neg"), autocast_exact)
+    if not (qr.dtype == pr.dtype == nr.dtype):     # mixed fp16 / fp32: the reference promotes to fp32
+        qr, pr, nr = [t.float() if t.dtype == torch.float16 else t for t in (qr, pr, nr)]
     _ops.check_same(qr, pr, "qry", "pos")
     _ops.check_same(qr, nr, "qry", "neg")
     if not (qr.shape == pr.shape == nr.shape):
@@ -144,9 +161,9 @@ def _triplet_rows(q, p, n):
 
 class _TripletLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, p, n, margin_cos, margin_con, mean, want_pairs, pair_eps):
+    def forward(ctx, q, p, n, margin_cos, margin_con, mean, want_pairs, pair_eps, autocast_exact=True):
         lib = _lib.load()
-        qr, pr, nr = _triplet_rows(q, p, n)
+        qr, pr, nr = _triplet_rows(q, p, n, autocast_exact)
         B, D = qr.shape
         dev = qr.device
         need_grad = any(ctx.needs_input_grad[:3])
@@ -192,12 +209,13 @@ class _TripletLossFn(torch.autograd.Function):
                                            _ops.stream_ptr(dev)), "irr_triplet_loss_bwd")
         ng = ctx.needs_input_grad
         return (dq.to(qd) if ng[0] else None, dp.to(pd) if ng[1] else None,
-                dn.to(nd) if ng[2] else None, None, None, None, None, None)
+                dn.to(nd) if ng[2] else None, None, None, None, None, None, None)
 
 
 def triplet_losses(qry: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, margin: float = 0.3, *,
                    margin_con: Optional[float] = None, mean: bool = True,
-                   pair_scores: bool = False, pair_eps: float = 1e-6) -> TripletLosses:
+                   pair_scores: bool = False, pair_eps: float = 1e-6,
+                   autocast_exact: bool = True) -> TripletLosses:
     """The four embedding-loss scalars of a training / validation step from ONE pass over the
     triplets, each differentiable:
 
@@ -206,10 +224,14 @@ def triplet_losses(qry: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, marg
 
     ``pair_scores=True`` also returns the row-wise ``cos(q_i,p_i)`` / ``cos(q_i,n_i)`` the
     reference logs as cos_sims / cos_unsims (train/train_efficient_cos_con_ce_loss.py:377-382).
+    fp16 triplets (``precision=16``) are read as fp16 and ``pos - qry`` / ``neg - qry`` are rounded
+    to fp16 like the reference's autocast does (``autocast_exact=False``: widened to fp32 first,
+    which is more exact than — so not identical to — the reference).
     """
     mc = float(margin)
     mk = float(margin if margin_con is None else margin_con)
-    out = _TripletLossFn.apply(qry, pos, neg, mc, mk, bool(mean), bool(pair_scores), float(pair_eps))
+    out = _TripletLossFn.apply(qry, pos, neg, mc, mk, bool(mean), bool(pair_scores), float(pair_eps),
+                               bool(autocast_exact))
     if pair_scores:
         return TripletLosses(out[0], out[1], out[2], out[3], out[4][0], out[4][1])
     return TripletLosses(out[0], out[1], out[2], out[3], None, None)
@@ -226,13 +248,14 @@ class TripletFwdBwd(NamedTuple):
 def triplet_losses_fwd_bwd(qry: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor,
                            margin: float = 0.3, *, margin_con: Optional[float] = None,
                            mean: bool = True, grad_scale: Sequence[float] = (1.0, 1.0, 1.0, 1.0),
-                           pair_scores: bool = False, pair_eps: float = 1e-6) -> TripletFwdBwd:
+                           pair_scores: bool = False, pair_eps: float = 1e-6,
+                           autocast_exact: bool = True) -> TripletFwdBwd:
     """Single-launch forward + backward: the four losses and the gradients of
     ``sum_j grad_scale[j] * loss_j`` w.r.t. qry / pos / neg, written in the same pass that reads the
     rows (2 x 3BD bytes of HBM traffic in total).  For training loops that own their backward; the
     autograd-integrated form is :func:`triplet_losses`."""
     lib = _lib.load()
-    qr, pr, nr = _triplet_rows(qry, pos, neg)
+    qr, pr, nr = _triplet_rows(qry, pos, neg, autocast_exact)
     B, D = qr.shape
     dev = qr.device
     losses = torch.empty(4, dtype=torch.float32, device=dev)

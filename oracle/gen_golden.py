@@ -66,6 +66,39 @@ def golden_losses(ContrastiveLoss):
     return out
 
 
+def golden_autocast(ContrastiveLoss):
+    """fp16 embeddings under precision=16 (train/train_efficient_cos_con_ce_loss.py:465): the
+    reference's `fm2 - fm1` (utils/contrastive_loss.py:56) is an fp16 subtraction; pow / sum and
+    cosine_embedding_loss are widened to fp32 by autocast.  CPU autocast has a
+    different op list, so the policy is applied by hand AROUND the unmodified reference module: it
+    is given fm1 = 0 and fm2 = the fp16-rounded difference (fm2 - fm1 is then exactly that
+    difference), i.e. the module evaluates precisely what it evaluates under CUDA autocast.
+    Tight positives (p = q + 0.002 randn) make the fp16 rounding of p - q matter (> 1e-5)."""
+    out = {}
+    B, D = 40, 96
+    q, p, n = synthetic.triplets(B, D, seed=17)
+    p = synthetic.unit(q + 0.002 * torch.randn(B, D, generator=torch.Generator().manual_seed(18)))
+    q16, p16, n16 = q.half(), p.half(), n.half()
+    out["ac_q"], out["ac_p"], out["ac_n"] = q16.numpy(), p16.numpy(), n16.numpy()
+    one, minus = torch.tensor(1.).unsqueeze(0), torch.tensor(-1.).unsqueeze(0)
+    zeros = torch.zeros(B, D)
+    for margin in (0.2, 0.3, 0.5):
+        qr, pr, nr = [t.clone().requires_grad_(True) for t in (q16, p16, n16)]
+        cos_loss = torch.nn.CosineEmbeddingLoss(margin=margin)
+        con_loss = ContrastiveLoss(margin=margin)
+        l = torch.stack([cos_loss(qr.float(), pr.float(), one), cos_loss(qr.float(), nr.float(), minus),
+                         con_loss(zeros, (pr - qr).float(), torch.tensor(1.).unsqueeze(0)),
+                         con_loss(zeros, (nr - qr).float(), torch.tensor(0.).unsqueeze(0))])
+        # GradScaler-style scale so that the fp16 gradients do not underflow (Lightning does this)
+        (1024.0 * l.sum()).backward()
+        key = f"ac_m{margin}"
+        out[key + "_losses"] = l.detach().numpy()
+        out[key + "_dq"], out[key + "_dp"], out[key + "_dn"] = qr.grad.numpy(), pr.grad.numpy(), nr.grad.numpy()
+        # the same module on the widened inputs: what a "more exact" implementation would return
+        out[key + "_con_pos_widened"] = np.float32(con_loss(q16.float(), p16.float(), 1.).item())
+    return out
+
+
 def golden_retrieval():
     out = {}
     cos = torch.nn.CosineSimilarity(dim=1, eps=1e-6)
@@ -166,6 +199,7 @@ def main():
     np.savez_compressed(OUT / "losses.npz", **golden_losses(ContrastiveLoss))
     np.savez_compressed(OUT / "retrieval.npz", **golden_retrieval())
     np.savez_compressed(OUT / "producer_consumer.npz", **golden_producer_consumer())
+    np.savez_compressed(OUT / "autocast.npz", **golden_autocast(ContrastiveLoss))
     for f in sorted(OUT.glob("*.npz")):
         print(f, f.stat().st_size, "bytes")
 

@@ -219,8 +219,9 @@ def four_losses(q: torch.Tensor, p: torch.Tensor, n: torch.Tensor, margin: float
                 margin_con: Optional[float] = None) -> torch.Tensor:
     """[cos_pos, cos_neg, con_pos, con_neg] exactly as training_step composes them
     (train/train_efficient_cos_con_ce_loss.py:230-237) with the [1]-shaped labels of :97-100."""
-    labels = {"con_pos": torch.tensor(1.).unsqueeze(0), "con_neg": torch.tensor(0.).unsqueeze(0),
-              "cos_pos": torch.tensor(1.).unsqueeze(0), "cos_neg": torch.tensor(-1.).unsqueeze(0)}
+    dev = q.device
+    labels = {"con_pos": torch.tensor(1., device=dev).unsqueeze(0), "con_neg": torch.tensor(0., device=dev).unsqueeze(0),
+              "cos_pos": torch.tensor(1., device=dev).unsqueeze(0), "cos_neg": torch.tensor(-1., device=dev).unsqueeze(0)}
     mk = margin if margin_con is None else margin_con
     cos_loss = torch.nn.CosineEmbeddingLoss(margin=margin)                              # :158
     return torch.stack([
@@ -239,6 +240,35 @@ def four_losses_and_grads(q, p, n, margin: float, weights=(1.0, 1.0, 1.0, 1.0),
     losses = four_losses(qr, pr, nr, margin, margin_con)
     w = torch.tensor(weights, dtype=dtype)
     (losses * w).sum().backward()
+    return losses.detach(), qr.grad, pr.grad, nr.grad
+
+
+def four_losses_autocast_fp16(q: torch.Tensor, p: torch.Tensor, n: torch.Tensor, margin: float,
+                              margin_con: Optional[float] = None) -> torch.Tensor:
+    """four_losses as the reference evaluates it on fp16 embeddings under ``precision=16``
+    (train/train_efficient_cos_con_ce_loss.py:465), with autocast's dtype policy written out so that
+    it runs on the CPU: ``fm2 - fm1`` (utils/contrastive_loss.py:56) is not on any autocast list and
+    runs in the inputs' dtype — an fp16 subtraction, rounded to fp16 — while ``pow``, ``sum`` and
+    ``cosine_embedding_loss`` are on the fp32 list: fp32 arithmetic on the fp16
+    values.  Differentiable w.r.t. fp16 leaves (the casts round the gradients to fp16 and fp16
+    ``.grad`` accumulates in fp16, as under autocast)."""
+    assert q.dtype == p.dtype == n.dtype == torch.float16
+    mk = margin if margin_con is None else margin_con
+    one, minus = torch.tensor(1.).unsqueeze(0), torch.tensor(-1.).unsqueeze(0)
+    cos_loss = torch.nn.CosineEmbeddingLoss(margin=margin)                              # :158, fp32 list
+    def con(a, b, label):                                                               # :56-61
+        dis = (b - a).float().pow(2).sum(1)               # fp16 sub, then the fp32-list ops
+        losses = 0.5 * (label * dis + (1 + -1 * label) * F.relu(mk - (dis + CONTRASTIVE_EPS).sqrt()).pow(2))
+        return losses.mean()
+    return torch.stack([cos_loss(q.float(), p.float(), one), cos_loss(q.float(), n.float(), minus),
+                        con(q, p, 1.0), con(q, n, 0.0)])
+
+
+def four_losses_and_grads_autocast_fp16(q, p, n, margin: float, weights=(1.0, 1.0, 1.0, 1.0),
+                                        margin_con: Optional[float] = None):
+    qr, pr, nr = [t.detach().clone().requires_grad_(True) for t in (q, p, n)]
+    losses = four_losses_autocast_fp16(qr, pr, nr, margin, margin_con)
+    (losses * torch.tensor(weights)).sum().backward()
     return losses.detach(), qr.grad, pr.grad, nr.grad
 
 

@@ -50,6 +50,12 @@ def golden_retrieval():
 
 
 @pytest.fixture(scope="session")
+def golden_autocast():
+    import numpy as np
+    return dict(np.load(GOLDEN / "autocast.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_pc():
     import numpy as np
     return dict(np.load(GOLDEN / "producer_consumer.npz"))

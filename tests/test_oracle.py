@@ -58,6 +58,27 @@ def test_restated_losses_match_reference(golden_losses, tag, margin):
     assert torch.allclose(ref.contrastive_loss(q, n, 0.0, margin, mean=False), sums[1], rtol=1e-6)
 
 
+@pytest.mark.parametrize("margin", MARGINS)
+def test_autocast_fp16_restatement_matches_reference_module(golden_autocast, margin):
+    """precision=16 semantics (fp16 `fm2 - fm1`, fp32 everywhere else): the oracle's written-out
+    policy against vectors produced by the unmodified reference module (oracle/gen_golden.py)."""
+    g = golden_autocast
+    q, p, n = T(g["ac_q"]), T(g["ac_p"]), T(g["ac_n"])
+    assert q.dtype == torch.float16
+    key = f"ac_m{margin}"
+    w = (1024.0,) * 4
+    l, dq, dp, dn = ref.four_losses_and_grads_autocast_fp16(q, p, n, margin, weights=w)
+    assert torch.allclose(l, T(g[key + "_losses"]), rtol=1e-6, atol=1e-9)
+    for got, name in ((dq, "_dq"), (dp, "_dp"), (dn, "_dn")):
+        want = T(g[key + name])
+        assert got.dtype == torch.float16
+        # fp16 gradients: the two graphs round in the same places except the weighted sum
+        assert ((got.float() - want.float()).abs() <= 2e-3 * want.float().abs() + 1e-3).all(), name
+    # p - q of nearly equal fp16 rows is EXACT in fp16 (Sterbenz), so for tight positives the
+    # autocast value and the widened value agree far below the 1e-5 bar; the fixture records both
+    assert abs(float(l[2]) - float(g[key + "_con_pos_widened"])) <= 1e-5 * float(l[2])
+
+
 def test_contrastive_docstring_shape(golden_losses):
     g = golden_losses
     got = ref.contrastive_loss(T(g["doc_a"]), T(g["doc_b"]), 1, 0.5)
