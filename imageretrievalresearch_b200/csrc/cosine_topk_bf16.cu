@@ -536,14 +536,17 @@ constexpr int P_A_BYTES = BLOCK_M * BLOCK_K * 2;               // 16 KB
 constexpr int P_B_BYTES = P_B_ROWS * BLOCK_K * 2;              // 16 KB
 constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;           // 32 KB
 constexpr int P_SMEM_TILES = P_STAGES * P_STAGE_BYTES;         // 196608
-// full / empty / norm-done / tile-landed per stage, accumulator full / empty / norms-published per
-// accumulator stage
-constexpr int P_SMEM_BARS = (4 * P_STAGES + 3 * ACC_STAGES) * 8;
+// full / empty / norm-done per stage, accumulator full / empty / norms-published per accumulator stage
+constexpr int P_SMEM_BARS = (3 * P_STAGES + 3 * ACC_STAGES) * 8;
 constexpr int P_SMEM_TOTAL = P_SMEM_TILES + SMEM_GN + P_SMEM_BARS + 16;
 constexpr int P_SMEM_ALLOC = P_SMEM_TOTAL + 1024;
 constexpr int P_THREADS = 256;
-constexpr int P_NORM_WARP0 = 8;            // warps 8-11 of the variants that make their own gallery norms
+// Warps of the variants that make their own gallery norms: 2, 3, 10 and 11 — the two schedulers
+// (warp id mod 4) that do NOT host the TMA producer (warp 0) and the MMA issuer (warp 1), whose
+// single-thread issue loops are the latency-critical part of the CTA; warps 8 and 9 stay idle.
 constexpr int P_THREADS_NORM = 384;
+__device__ __forceinline__ bool is_norm_warp(int warp) { return (warp & 2) && (warp < 4 || warp >= 8); }
+__device__ __forceinline__ int norm_warp_index(int warp) { return warp < 4 ? warp - 2 : warp - 8; }
 // where the pair kernel's inverse gallery norms come from
 constexpr int NORMS_CACHED = 0;      // g_inv_norm (the caller's Gallery cache)
 constexpr int NORMS_PRODUCERS = 1;   // grid-wide in-kernel producers reading global memory (>= 3 pairs)
@@ -665,12 +668,11 @@ __device__ __forceinline__ void norm_row_sums(const uint4* r, int nt, float& sa,
 //
 // NORMS_FUSED (no cached norms, one or two query-tile pairs): L2-normalisation fused into the load.
 // Four extra warps per CTA square-sum the CTA's half of every gallery tile out of the SAME
-// shared-memory stages the MMAs read, while the MMAs read them: the leader's norm warps wait on
-// the stage's "full" barrier like the MMA issuer; both CTAs' loads complete on that barrier, which
-// lives in the leader, so one leader lane forwards the event to the partner's "tile landed"
-// barrier (a remote arrive) for the partner's norm warps.  The TMA producer refills a stage once
-// its MMAs retired AND the CTA's norm warps are done with it ("norm done" barrier).  The norm
-// warps publish 1/max(|g|,eps) of
+// shared-memory stages the MMAs read — after the stage's MMAs retired (they wait on the stage's
+// "empty" barrier, which tcgen05.commit multicasts to both CTAs; the "full" barriers live in the
+// leader only, and forwarding them to the partner in software measured 2x slower) and before the
+// TMA producer may refill it (it also waits on the stage's "norm done" barrier) — and publish
+// 1/max(|g|,eps) of
 // their 128 rows into BOTH CTAs' norm buffers (own shared memory + a DSMEM store to the partner),
 // arriving on both CTAs' "norms published" barrier.  The gallery crosses HBM once, nothing is
 // exchanged through global memory and no CTA waits for a CTA outside its own cluster.  With many
@@ -712,7 +714,6 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + ACC_STAGES + s); };
   auto gnfull_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + 2 * ACC_STAGES + s); };
   auto normdone_bar = [&](int s) { return bars + 8u * (2 * P_STAGES + 3 * ACC_STAGES + s); };
-  auto landed_bar = [&](int s) { return bars + 8u * (3 * P_STAGES + 3 * ACC_STAGES + s); };
   const uint32_t tmem_slot = bars + P_SMEM_BARS;
   float* gn_smem = reinterpret_cast<float*>(smem_gen + P_SMEM_TILES);
   volatile uint32_t* tmem_slot_gen =
@@ -744,10 +745,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(tempty_bar(s), 2 * (EPI_THREADS / 32));  // 4 epilogue warps of each CTA (leader's copy)
       mbar_init(gnfull_bar(s), 2 * (NORM_THREADS / 32)); // NORMS_FUSED: 4 norm warps of each CTA
     }
-    for (int s = 0; s < P_STAGES; ++s) {
-      mbar_init(normdone_bar(s), NORM_THREADS / 32);
-      mbar_init(landed_bar(s), 1);   // NORMS_FUSED, non-leader CTA: the leader forwards "stage full"
-    }
+    for (int s = 0; s < P_STAGES; ++s) mbar_init(normdone_bar(s), NORM_THREADS / 32);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
@@ -833,11 +831,11 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     }
-  } else if (NORMS == NORMS_FUSED && warp >= P_NORM_WARP0) {
+  } else if (NORMS == NORMS_FUSED && is_norm_warp(warp)) {
     // ===================== fused gallery norms (this CTA's half of every tile) ===============
     // thread nt owns gallery row rank*128 + nt of the tile: one 128-byte slice per stage, read in
     // logical chunk order (conflict-free, position independent — see the single-CTA kernel)
-    const int nt = threadIdx.x - P_NORM_WARP0 * 32;
+    const int nt = norm_warp_index(warp) * 32 + lane;
     const uint32_t peer = rank ^ 1u;
     const bool f16 = is_f16 != 0;
     int stage = 0;
@@ -850,12 +848,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (int t = t0; t < t1; ++t, ++it) {
         float sa = 0.f, sb = 0.f;
         for (int kb = 0; kb < num_kb; ++kb) {
-          if (rank == 0) {
-            mbar_wait(full_bar(stage), phase, 1500 + stage);          // both CTAs' tiles have landed
-            if (warp == P_NORM_WARP0 && lane == 0) mbar_arrive_cluster(mapa_rank(landed_bar(stage), 1));
-          } else {
-            mbar_wait_cluster(landed_bar(stage), phase, 1550 + stage);
-          }
+          mbar_wait(empty_bar(stage), phase, 1500 + stage);   // the stage's MMAs have retired
           const uint4* r = reinterpret_cast<const uint4*>(smem_gen + stage * P_STAGE_BYTES + P_A_BYTES + nt * 128);
           if (f16) norm_row_sums<true>(r, nt, sa, sb);
           else     norm_row_sums<false>(r, nt, sa, sb);
@@ -879,9 +872,9 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     }
-  } else if (NORMS_INSIDE && warp >= P_NORM_WARP0) {
+  } else if (NORMS_INSIDE && is_norm_warp(warp)) {
     // ===================== gallery-norm producers (whole grid, need order) =====================
-    const int nw = static_cast<int>(blockIdx.x) * 4 + (warp - P_NORM_WARP0);
+    const int nw = static_cast<int>(blockIdx.x) * 4 + norm_warp_index(warp);
     const int NW = static_cast<int>(gridDim.x) * 4;
     // Slots (one octet of rows each) in the order the tile stream needs them: wave by wave (a wave
     // = one unit per cluster), inside a wave tile by tile, inside a tile position the chunks whose
@@ -925,7 +918,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         atomicAdd(tile_rows_done + tile, static_cast<uint32_t>(rows));
       }
     }
-  } else if (warp >= EPI_WARP0 && warp < P_NORM_WARP0) {
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
     // ===================== epilogue (both CTAs: own 128 query rows x 256 columns) ==========
     const int ew = warp - EPI_WARP0;
     const int et = threadIdx.x - EPI_WARP0 * 32;

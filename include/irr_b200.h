@@ -20,6 +20,9 @@
  *   - row-major contiguous embeddings, row stride == D elements; base pointers 16-byte aligned;
  *     D % 8 == 0 for IRR_BF16 / IRR_F16 and D % 4 == 0 for IRR_F32 (1536 / 1920 / 2560 in the reference).
  *   - re-entrant and thread-safe for distinct streams + workspaces.
+ *   - kernels that wait for CTAs outside their own cluster (uncached searches of more than 512
+ *     queries; the fused exchange+merge) are launched cooperatively; when the driver cannot make
+ *     the grid co-resident the call takes an equivalent path that needs no co-residency.
  *   - there is no CPU fallback: a device that is not sm_100 makes the bf16 tensor path return
  *     IRR_ERR_UNSUPPORTED_DEVICE.
  */
@@ -54,10 +57,12 @@ enum {
   IRR_ERR_ROW_TOO_LONG = -7        /* D too large for the shared-memory staged loss kernels */
 };
 
-/* IRR_F16 is accepted only where stated: feature maps and logits produced under fp16 autocast, and
- * the rows of irr_cosine_topk / irr_cosine_topk_sharded / irr_row_inv_norms / irr_pair_cosine (the
- * embeddings the reference's precision=16 training produces,
- * train/train_efficient_cos_con_ce_loss.py:465) */
+/* IRR_F16: the embeddings the reference's precision=16 training produces
+ * (train/train_efficient_cos_con_ce_loss.py:465), feature maps and logits produced under fp16
+ * autocast.  Search / similarity entry points read the fp16 values exactly; the loss entry points
+ * reproduce autocast's arithmetic on them: b - a of the contrastive distance is an fp16
+ * subtraction (utils/contrastive_loss.py:56 is not on an autocast list), everything else fp32
+ * (pow, sum, cosine_embedding_loss are on the fp32 list); gradients are emitted in fp16. */
 typedef enum { IRR_F32 = 0, IRR_BF16 = 1, IRR_F16 = 2 } irr_dtype;
 
 /* largest k of irr_cosine_topk; up to IRR_MAX_K_FUSED the register-resident epilogues select inside
@@ -92,7 +97,10 @@ IRR_API const char* irr_status_string(irr_status s);
  *             NULL = computed inside the call.
  * out_val [Q,k] fp32 sorted descending, ties broken by LOWER gallery index;
  * out_idx [Q,k] int64 = local row index + idx_offset (idx_offset = first row of this shard).
- * Slots beyond N (k > N) hold (-inf, -1).   1 <= k <= IRR_MAX_K.
+ * Slots beyond N (k > N, N == 0 included) hold (-inf, -1).   1 <= k <= IRR_MAX_K.
+ * Non-finite inputs follow torch: a gallery row with a NaN / Inf element scores NaN against every
+ * query, NaN orders ABOVE every number (torch.topk's rule), so those rows come first, lower index
+ * first; a non-finite query row yields k NaN values (which rows: unspecified, as in torch).
  * For k <= IRR_MAX_K_FUSED the Q x N score matrix is never written to memory.
  * ------------------------------------------------------------------------------------------ */
 IRR_API size_t irr_cosine_topk_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t k,

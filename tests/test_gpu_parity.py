@@ -198,7 +198,9 @@ def test_fp16_triplets_reproduce_the_reference_under_autocast(golden_autocast, m
     w = (1024.0,) * 4                                  # the fixture's loss scale (fp16 gradients)
     out = irr.triplet_losses_fwd_bwd(q, p, n, margin, grad_scale=w)
     assert out.grad_qry.dtype == torch.float16
-    assert ((out.losses - want).abs() <= LOSS_REL * want.abs() + 1e-9).all(), (out.losses, want)
+    # cos_pos = mean(1 - c) with c ~ 0.9998 on this fixture (tight positives): fp32 round-off of c
+    # itself (6e-8) bounds what any two fp32 evaluations can agree on, hence the absolute term
+    assert ((out.losses - want).abs() <= LOSS_REL * want.abs() + 1e-7).all(), (out.losses, want)
     for got, name in ((out.grad_qry, "_dq"), (out.grad_pos, "_dp"), (out.grad_neg, "_dn")):
         # fp16 storage: 2^-11 per element, and the reference accumulates its two fp16 gradient
         # contributions in fp16 where the kernel rounds their fp32 sum once
