@@ -24,7 +24,7 @@ def main():
     dem = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.split("\n")
     rows, total = [], collections.Counter()
     for f, d in zip(funcs, dem):
-        ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]*)", f)
+        ops = re.findall(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]*)", f)
         c = collections.Counter()
         for op in ops:
             for col in COLS:
