@@ -27,7 +27,6 @@ SIGNATURES = {
     "irr_status_string": (C.c_char_p, [_i32]),
     "irr_profile_next_topk": (None, [_vp, _vp]),
     "irr_debug_occupy_sms": (_i32, [_i32, _i32, _i64, _vp]),
-    "irr_debug_set_cluster_size": (None, [_i32]),
     "irr_cosine_topk_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "irr_cosine_topk": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i64, _vp, _vp,
                                _vp, _sz, _vp]),

@@ -67,9 +67,7 @@ struct Knobs {
   int producers_min_pairs;   // IRR_NORMS_MIN_PAIRS: query-tile pairs from which the producers are used
   int norm_ahead;            // IRR_NORM_AHEAD: tiles the producers may run ahead (negative = unpaced)
   bool fused_pair;           // IRR_FUSED_PAIR=0: no fused norms in the pair kernel (pre-pass instead)
-  int cluster;               // IRR_CLUSTER=2|4: CTAs per cluster of the pair kernel (0 = by batch size)
 };
-std::atomic<int> g_cluster_override{-1};   // irr_debug_set_cluster_size (tests): -1 = follow the knob
 const Knobs& knobs() {
   static const Knobs k = []() {
     auto num = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
@@ -82,7 +80,6 @@ const Knobs& knobs() {
     r.producers_min_pairs = num("IRR_NORMS_MIN_PAIRS", 3);
     r.norm_ahead = num("IRR_NORM_AHEAD", 2);
     r.fused_pair = !flag("IRR_FUSED_PAIR", '0');
-    r.cluster = num("IRR_CLUSTER", 0);
     return r;
   }();
   return k;
@@ -693,16 +690,8 @@ __device__ __forceinline__ void norm_row_sums(const uint4* r, int nt, float& sa,
 // the launch and the host falls back to the pre-pass), so the waits cannot deadlock; they trap on a
 // 4 s watchdog like the mbarriers.  Measured: neutral at Q=4096 (the chip is at its power cap: the
 // same joules take the same time wherever they are spent), a clear win for 257..2048 queries.
-//
-// CL = CTAs per cluster: 2 (one CTA pair), or 4 = two CTA pairs that walk the SAME gallery tiles in
-// lockstep with their own 256 query rows each.  The gallery tile is then fetched once per cluster:
-// every CTA loads one quarter (64 rows) and TMA-multicasts it into its own shared memory and into
-// the CTA of the other pair that holds the same half, so L2 -> SM traffic per flop drops by a
-// quarter (per 512 x 256 x 64 MACs: 64 KB of query tiles + 32 KB of gallery tile instead of
-// 64 + 64).  A stage is free for the cluster's producers once BOTH pairs' MMAs on it retired
-// (each leader's tcgen05.commit is multicast to all four CTAs' "empty" barriers).
-template <int KMAX, int NORMS, int CL>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NORMS != NORMS_CACHED ? P_THREADS_NORM : P_THREADS, 1)
+template <int KMAX, int NORMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NORMS != NORMS_CACHED ? P_THREADS_NORM : P_THREADS, 1)
 cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                              const __grid_constant__ CUtensorMap tmap_q_tail,
                              const __grid_constant__ CUtensorMap tmap_g,
@@ -737,12 +726,9 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();  // rank in the cluster, 0 .. CL-1
-  const uint32_t rank = crank & 1u;          // position in the CTA pair, 0 = the pair's leader
-  const uint32_t lead = crank & ~1u;         // cluster rank of this pair's leader
-  const uint32_t pp = crank >> 1;            // which pair of the cluster
-  const int cluster_id = blockIdx.x / CL;
-  const int num_clusters = gridDim.x / CL;
+  const uint32_t rank = cluster_ctarank();   // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -752,7 +738,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < P_STAGES; ++s) {
       mbar_init(full_bar(s), 1);    // leader's own arrive.expect_tx; bytes come from both CTAs
-      mbar_init(empty_bar(s), CL / 2);   // one multicast tcgen05.commit per pair of the cluster
+      mbar_init(empty_bar(s), 1);   // one multicast tcgen05.commit
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);                        // one multicast tcgen05.commit
@@ -764,7 +750,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
   if (warp == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
   tcgen05_fence_before();
-  cluster_sync_all();   // barrier inits + TMEM allocation visible to every CTA of the cluster
+  cluster_sync_all();   // barrier inits + TMEM allocation visible to both CTAs
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -783,10 +769,10 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     };
     for (int u = cluster_id; u < total_units; u += num_clusters) {
       const int chunk = u / m_pairs, mp = u - chunk * m_pairs;
-      const int mt = mp * CL + static_cast<int>(crank);
+      const int mt = mp * 2 + static_cast<int>(rank);
       const int t0 = chunk * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
-      const uint32_t stage_tx = a_bytes(mp * CL + lead) + a_bytes(mp * CL + lead + 1) + 2 * P_B_BYTES;
+      const uint32_t stage_tx = a_bytes(mp * 2) + a_bytes(mp * 2 + 1) + 2 * P_B_BYTES;
       const int my_a = a_bytes(mt);
       for (int t = t0; t < t1; ++t) {
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -796,23 +782,13 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (lane == 0) {
             const uint32_t a_dst = smem_base + stage * P_STAGE_BYTES;
             const uint32_t b_dst = a_dst + P_A_BYTES;
-            const uint32_t lead_full = mapa_rank(full_bar(stage), lead);
+            const uint32_t lead_full = mapa_rank(full_bar(stage), 0);
             if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), stage_tx);
             if (my_a)
               tma_load_2d_pair(a_dst, mt == tail_tile ? &tmap_q_tail : &tmap_q, kb * BLOCK_K,
                                mt * BLOCK_M, lead_full, kPolicyEvictLast);
-            if (CL == 2) {
-              tma_load_2d_pair(b_dst, &tmap_g, kb * BLOCK_K, t * BLOCK_N + static_cast<int>(rank) * P_B_ROWS,
-                               lead_full, kPolicyEvictNormal);
-            } else {
-              // this CTA's quarter of the gallery tile (64 rows of half `rank`), delivered to the
-              // CTA holding that half in each pair
-              constexpr int QROWS = P_B_ROWS / (CL / 2);
-              tma_load_2d_pair_mcast(b_dst + pp * (QROWS * BLOCK_K * 2), &tmap_g, kb * BLOCK_K,
-                                     t * BLOCK_N + static_cast<int>(rank) * P_B_ROWS + static_cast<int>(pp) * QROWS,
-                                     lead_full, static_cast<uint16_t>((1u << rank) | (1u << (rank + 2))),
-                                     kPolicyEvictNormal);
-            }
+            tma_load_2d_pair(b_dst, &tmap_g, kb * BLOCK_K, t * BLOCK_N + static_cast<int>(rank) * P_B_ROWS,
+                             lead_full, kPolicyEvictNormal);
           }
           __syncwarp();
           if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
@@ -826,8 +802,6 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      const uint16_t all_ctas = static_cast<uint16_t>((1u << CL) - 1u);   // "stage free": whole cluster
-      const uint16_t my_pair = static_cast<uint16_t>(0x3u << lead);       // "accumulator ready": own pair
       for (int u = cluster_id; u < total_units; u += num_clusters) {
         const int chunk = u / m_pairs;
         const int t0 = chunk * tiles_per_chunk;
@@ -848,8 +822,8 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
               for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
                 umma_bf16_ss_pair(tmem_d, adesc + 2u * kk, bdesc + 2u * kk, idesc,
                                   (kb > 0 || kk > 0) ? 1u : 0u);
-              umma_commit_pair(empty_bar(stage), all_ctas);
-              if (kb == num_kb - 1) umma_commit_pair(tfull_bar(as), my_pair);
+              umma_commit_pair(empty_bar(stage), 0x3);
+              if (kb == num_kb - 1) umma_commit_pair(tfull_bar(as), 0x3);
             }
             __syncwarp();
             if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
@@ -862,7 +836,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // thread nt owns gallery row rank*128 + nt of the tile: one 128-byte slice per stage, read in
     // logical chunk order (conflict-free, position independent — see the single-CTA kernel)
     const int nt = norm_warp_index(warp) * 32 + lane;
-    const uint32_t peer = crank ^ 1u;
+    const uint32_t peer = rank ^ 1u;
     const bool f16 = is_f16 != 0;
     int stage = 0;
     uint32_t phase = 0;
@@ -893,8 +867,8 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         st_shared_cluster_f32(mapa_rank(smem_u32(mine), peer), inv);
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive_cluster(mapa_rank(gnfull_bar(as), lead));
-          mbar_arrive_cluster(mapa_rank(gnfull_bar(as), lead + 1));
+          mbar_arrive_cluster(mapa_rank(gnfull_bar(as), 0));
+          mbar_arrive_cluster(mapa_rank(gnfull_bar(as), 1));
         }
       }
     }
@@ -954,7 +928,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     uint32_t it = 0;
     for (int u = cluster_id; u < total_units; u += num_clusters) {
       const int chunk = u / m_pairs, mp = u - chunk * m_pairs;
-      const int mt = mp * CL + static_cast<int>(crank);
+      const int mt = mp * 2 + static_cast<int>(rank);
       const int t0 = chunk * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
       const int row = mt * BLOCK_M + row_in_tile;
@@ -994,8 +968,8 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive_cluster(mapa_rank(tempty_bar(as), lead));
-          if (NORMS == NORMS_FUSED) mbar_arrive_cluster(mapa_rank(tempty_bar(as), lead + 1));
+          mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));
+          if (NORMS == NORMS_FUSED) mbar_arrive_cluster(mapa_rank(tempty_bar(as), 1));
         }
       }
       if (row < Q) {
@@ -1023,18 +997,11 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
 }
 
-// Clusters of CL CTAs of the pair kernel the device holds at once (one CTA per SM).  Pairs always
-// tile the SMs (a TPC is two SMs); clusters of four need four free SMs inside one GPC, so a few
-// SMs can stay empty: asked of the occupancy calculator once.
-template <int CL>
-int resident_clusters();
-template <>
-int resident_clusters<2>() { return num_sms() / 2; }
-
-// chunking for the pair kernel: units = (group of CL query tiles, gallery chunk) over the clusters
-Plan make_plan_pair(int64_t Q, int64_t N, int CL, int clusters) {
+// chunking for the pair kernel: units = (query-tile pair, gallery chunk) over sms/2 clusters
+Plan make_plan_pair(int64_t Q, int64_t N) {
   Plan p;
-  p.m_tiles = static_cast<int>((Q + CL * BLOCK_M - 1) / (CL * BLOCK_M));  // groups of CL query tiles
+  const int clusters = num_sms() / 2;
+  p.m_tiles = static_cast<int>((Q + 2 * BLOCK_M - 1) / (2 * BLOCK_M));  // pairs of query tiles
   p.n_tiles = static_cast<int>((N + BLOCK_N - 1) / BLOCK_N);
   if (p.n_tiles < 1) p.n_tiles = 1;
   int best_tpc = 1;
@@ -1052,7 +1019,7 @@ Plan make_plan_pair(int64_t Q, int64_t N, int CL, int clusters) {
   p.tiles_per_chunk = best_tpc;
   p.n_chunks = (p.n_tiles + best_tpc - 1) / best_tpc;
   const long long units = 1ll * p.n_chunks * p.m_tiles;
-  p.grid = CL * static_cast<int>(units < clusters ? units : clusters);
+  p.grid = 2 * static_cast<int>(units < clusters ? units : clusters);
   return p;
 }
 
@@ -1071,49 +1038,13 @@ bool use_pair(int64_t Q, bool cached_norms) {
   return true;
 }
 
-template <>
-int resident_clusters<4>() {
-  static const int cached = []() {
-    auto kern = cosine_topk_bf16_pair_kernel<4, NORMS_PRODUCERS, 4>;
-    int n = 0;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(4 * (num_sms() / 4));
-    cfg.blockDim = dim3(P_THREADS_NORM);
-    cfg.dynamicSmemBytes = P_SMEM_ALLOC;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC) != cudaSuccess ||
-        cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
-      cudaGetLastError();
-      n = num_sms() / 4;   // no device (build box): only the workspace-size queries get here
-    }
-    return n;
-  }();
-  return cached;
-}
-
-// Measured on B200 (profiles/): which cluster size a batch of more than 256 queries gets by default
-int default_cluster_size(int64_t Q) {
-  (void)Q;
-  return 2;
-}
-
-// CTAs per cluster of the pair kernel: two pairs sharing every gallery tile by TMA multicast pay
-// off where a tile has at least two consumers and the L2 -> SM path is the limit (IRR_CLUSTER /
-// irr_debug_set_cluster_size override)
-int pair_cluster_size(int64_t Q) {
-  int c = g_cluster_override.load(std::memory_order_relaxed);
-  if (c < 0) c = knobs().cluster;
-  if (Q <= 2 * BLOCK_M) return 2;          // a single pair has nobody to share with
-  if (c == 2 || c == 4) return c;
-  return default_cluster_size(Q);
-}
-
-// norm source of an uncached pair launch: grid-wide producers above 512 queries (every pair
-// recomputing the norms of the tiles it streams would cost 16x the arithmetic at Q=4096), norms
-// fused into the tile stream up to 512 (the tile stream outruns four producer warps per CTA there:
-// measured 512 queries 1.69 vs 1.66 ms with the pre-pass, 768 queries 2.14 vs 2.54 ms)
-int pair_norm_mode(bool cached, int64_t Q) {
+// norm source of an uncached pair launch: grid-wide producers from three query-tile pairs on
+// (every pair recomputing the norms of the tiles it streams would cost 16x the arithmetic at
+// Q=4096), norms fused into the tile stream below (the tile stream outruns four producer warps per
+// CTA there: measured 512 queries 1.69 vs 1.66 ms with the pre-pass, 768 queries 2.14 vs 2.54 ms)
+int pair_norm_mode(bool cached, int m_pairs) {
   if (cached) return NORMS_CACHED;
-  if (knobs().producers && Q > 2ll * BLOCK_M * (knobs().producers_min_pairs - 1)) return NORMS_PRODUCERS;
+  if (knobs().producers && m_pairs >= knobs().producers_min_pairs) return NORMS_PRODUCERS;
   return knobs().fused_pair ? NORMS_FUSED : NORMS_CACHED;   // CACHED here = streaming pre-pass first
 }
 
@@ -1135,13 +1066,13 @@ void attr_set(std::atomic<uint64_t>& done) {
 // whole grid resident (also under MPS partitions, green contexts or with SMs held by kernels of
 // other streams) or refuses the launch — reported to the caller as *refused = true, which then
 // takes the pre-pass instead.  The other variants only wait inside their own cluster.
-template <int KMAX, int NORMS, int CL>
+template <int KMAX, int NORMS>
 irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float* gin, int64_t Q,
                        int64_t N, int32_t D, int32_t k, const Plan& p, float* pv, int32_t* pi,
                        uint32_t* row_floor, bool f16, const void* g, float eps, uint32_t* tile_done,
                        cudaStream_t st, bool* refused, const QueryMaps& qm) {
   const CUtensorMap& tqt = qm.tail;
-  auto kern = cosine_topk_bf16_pair_kernel<KMAX, NORMS, CL>;
+  auto kern = cosine_topk_bf16_pair_kernel<KMAX, NORMS>;
   static std::atomic<uint64_t> attr_done{0};
   if (attr_needed(attr_done)) {
     IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
@@ -1293,13 +1224,9 @@ size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
   // the caller may or may not pass cached norms: size for the larger of the two plans
   size_t parts = 0;
   for (int cached = 0; cached < 2; ++cached) {
-    for (int cl = 2; cl <= 4; cl += 2) {   // (the cluster size can be overridden at run time)
-      const Plan p = use_pair(Q, cached)
-                         ? make_plan_pair(Q, N, cl, cl == 4 ? resident_clusters<4>() : resident_clusters<2>())
-                         : make_plan(Q, N);
-      const size_t n = static_cast<size_t>(p.n_chunks) * Q * k;
-      if (n > parts) parts = n;
-    }
+    const Plan p = use_pair(Q, cached) ? make_plan_pair(Q, N) : make_plan(Q, N);
+    const size_t n = static_cast<size_t>(p.n_chunks) * Q * k;
+    if (n > parts) parts = n;
   }
   const size_t n_tiles = static_cast<size_t>((N + BLOCK_N - 1) / BLOCK_N);
   return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 +
@@ -1316,9 +1243,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   if (ws_bytes < bf16_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
   const bool cached = g_inv_norm != nullptr;
   const bool pair = use_pair(Q, cached);
-  const int CL = pair ? pair_cluster_size(Q) : 2;
-  const Plan p = pair ? make_plan_pair(Q, N, CL, CL == 4 ? resident_clusters<4>() : resident_clusters<2>())
-                      : make_plan(Q, N);
+  const Plan p = pair ? make_plan_pair(Q, N) : make_plan(Q, N);
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* gin_ws = reinterpret_cast<float*>(w);
   w += align_up(static_cast<size_t>(N) * 4, 256);
@@ -1330,7 +1255,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   uint32_t* row_floor = reinterpret_cast<uint32_t*>(w);
   w += align_up(static_cast<size_t>(Q) * 4, 256);
   uint32_t* tile_done = reinterpret_cast<uint32_t*>(w);
-  int mode = pair ? pair_norm_mode(cached, Q) : NORMS_CACHED;
+  int mode = pair ? pair_norm_mode(cached, p.m_tiles) : NORMS_CACHED;
   // one memset: the rows' shared floors and (if used) the per-tile norm counters
   IRR_CUDA_TRY(cudaMemsetAsync(
       row_floor, 0,
@@ -1341,18 +1266,15 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   QueryMaps qm;
   CUtensorMap tg;
   if (!encode_queries(&qm, q, Q, D, f16) ||
-      !encode_bf16_rows(&tg, g, N, D, pair ? P_B_ROWS / (CL / 2) : BLOCK_N, f16))
+      !encode_bf16_rows(&tg, g, N, D, pair ? P_B_ROWS : BLOCK_N, f16))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   const CUtensorMap& tq = qm.full;
   irr_status s = IRR_OK;
   if (pair) {
     const bool small_k = k <= 4;
     bool refused = false;
-#define IRR_LAUNCH_PAIR(KM, NM, GIN)                                                                  \
-  s = CL == 4 ? launch_pair<KM, NM, 4>(tq, tg, GIN, Q, N, D, k, p, pv, pi, row_floor, f16, g, eps,    \
-                                       tile_done, st, &refused, qm)                                   \
-              : launch_pair<KM, NM, 2>(tq, tg, GIN, Q, N, D, k, p, pv, pi, row_floor, f16, g, eps,    \
-                                       tile_done, st, &refused, qm)
+#define IRR_LAUNCH_PAIR(KM, NM, GIN) \
+  s = launch_pair<KM, NM>(tq, tg, GIN, Q, N, D, k, p, pv, pi, row_floor, f16, g, eps, tile_done, st, &refused, qm)
     if (mode == NORMS_PRODUCERS) {   // gin_ws is written by the kernel's own norm producers
       if (small_k) IRR_LAUNCH_PAIR(4, NORMS_PRODUCERS, gin_ws); else IRR_LAUNCH_PAIR(16, NORMS_PRODUCERS, gin_ws);
       if (s == IRR_OK && refused) mode = NORMS_CACHED;   // no co-resident grid: pre-pass instead
@@ -1388,10 +1310,6 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   }
   if (s != IRR_OK) return s;
   return merge_partials(pv, pi, p.n_chunks, Q, k, q, D, dt, eps, idx_offset, out_val, out_idx, st);
-}
-
-void bf16_set_cluster_override(int cluster) {
-  g_cluster_override.store(cluster == 2 || cluster == 4 ? cluster : -1, std::memory_order_relaxed);
 }
 
 irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N, int32_t D,

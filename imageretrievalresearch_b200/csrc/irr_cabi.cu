@@ -149,8 +149,6 @@ irr_status irr_debug_occupy_sms(int32_t ctas, int32_t smem_bytes, int64_t nanose
   return IRR_OK;
 }
 
-void irr_debug_set_cluster_size(int32_t ctas_per_cluster) { bf16_set_cluster_override(ctas_per_cluster); }
-
 const char* irr_status_string(irr_status s) {
   switch (s) {
     case IRR_OK: return "ok";

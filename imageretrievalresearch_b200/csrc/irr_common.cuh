@@ -332,20 +332,6 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* 
       "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster_addr), "l"(cache_policy)
       : "memory");
 }
-// The same load delivered to every CTA of `cta_mask` at the same shared-memory offset, issued by
-// one CTA of a cluster of several CTA pairs that share an operand tile (the bytes cross L2 -> SM
-// once).  In each destination CTA the completion is accounted on the mbarrier at the same offset
-// in that CTA's OWN pair leader (the peer bit of `bar_leader_addr` is clear: the issuing CTA's
-// leader barrier address), which is how every pair's MMA issuer sees the shared tile arrive.
-__device__ __forceinline__ void tma_load_2d_pair_mcast(uint32_t smem_dst, const void* tmap, int c0, int c1,
-                                                       uint32_t bar_leader_addr, uint16_t cta_mask,
-                                                       uint64_t cache_policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      ".multicast::cluster.L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(smem_dst),
-      "l"(tmap), "r"(bar_leader_addr), "h"(cta_mask), "r"(c0), "r"(c1), "l"(cache_policy)
-      : "memory");
-}
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_slot) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot),

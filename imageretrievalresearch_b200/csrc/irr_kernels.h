@@ -51,8 +51,6 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
 irr_status bf16_cosine_scores(const void* q, const void* g, int64_t Q, int64_t N, int32_t D,
                               float eps, float* out_scores, void* ws, size_t ws_bytes,
                               cudaStream_t st);
-// test aid: force the CTA-pair kernel's cluster size (2 or 4; anything else = default choice)
-void bf16_set_cluster_override(int cluster);
 
 irr_status bf16_scores_block(const void* q, const void* g, const float* g_inv_norm,
                              const float* q_inv_norm, int64_t Q, int64_t N, int32_t D, float eps,

@@ -124,11 +124,7 @@ IRR_API irr_status irr_cosine_topk(const void* q, const void* g, const float* g_
  *
  * irr_debug_occupy_sms: launch `ctas` CTAs that each hold `smem_bytes` of shared memory and spin
  * for `nanoseconds` (<= 2 s) on `stream` — a stand-in for a foreign kernel holding SMs, used by the
- * test that the persistent kernels neither hang nor trap when the GPU is not theirs alone.
- *
- * irr_debug_set_cluster_size: force the tensor-core kernel of batches above 256 queries to run in
- * clusters of 2 (one CTA pair) or 4 CTAs (two pairs sharing each gallery tile by TMA multicast);
- * any other value restores the library's own choice.  Process-wide; for tests and profiles/. */
+ * test that the persistent kernels neither hang nor trap when the GPU is not theirs alone. */
 IRR_API irr_status irr_cosine_scores_bf16(const void* q, const void* g, int64_t Q, int64_t N,
                                           int32_t D, float eps, float* out_scores,
                                           void* workspace, size_t workspace_bytes,
@@ -136,7 +132,6 @@ IRR_API irr_status irr_cosine_scores_bf16(const void* q, const void* g, int64_t 
 IRR_API void irr_profile_next_topk(void* ev_start, void* ev_stop);
 IRR_API irr_status irr_debug_occupy_sms(int32_t ctas, int32_t smem_bytes, int64_t nanoseconds,
                                         irr_stream_t stream);
-IRR_API void irr_debug_set_cluster_size(int32_t ctas_per_cluster);
 
 /* 1/max(|row|,eps) for every row of x [N,D] -> out fp32[N]; what a gallery handle caches. */
 IRR_API irr_status irr_row_inv_norms(const void* x, int64_t N, int32_t D, irr_dtype dt, float eps,

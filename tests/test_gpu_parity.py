@@ -486,33 +486,6 @@ def test_dispatch_regime_sweep(Q, D, N):
         assert (unc.values[:, 0] == unc.values[:, 1]).all()
 
 
-@pytest.mark.parametrize("Q,N,D", [(257, 20_011, 1536), (384, 9_001, 64), (512, 30_000, 1536),
-                                   (513, 20_011, 2560), (768, 50_000, 256), (1100, 40_003, 1536),
-                                   (4096, 70_001, 1536)])
-def test_cluster_of_four_with_multicast_matches_the_pair_kernel(Q, N, D):
-    """cosine_topk_bf16_pair_kernel<KM, *, 4>: two CTA pairs per cluster sharing every gallery
-    tile through TMA multicast (forced with the irr_debug_set_cluster_size test aid) must return
-    bit for bit what clusters of one pair return — same MMAs, same norm arithmetic, different
-    work split — for cached, fused and producer norms, k = 3 and 10, ragged query tiles, and both
-    must match the oracle."""
-    lib = _lib.load()
-    q, gal = synthetic.tied_gallery(N, D, Q, seed=Q + D, dtype=torch.bfloat16)
-    qd, gd = q.cuda(), gal.cuda()
-    handle = irr.Gallery(gd)
-    try:
-        for k in (3, 10):
-            lib.irr_debug_set_cluster_size(2)
-            want_u, want_c = irr.cosine_topk(qd, gd, k), handle.search(qd, k)
-            lib.irr_debug_set_cluster_size(4)
-            got_u, got_c = irr.cosine_topk(qd, gd, k), handle.search(qd, k)
-            for got, want in ((got_u, want_u), (got_c, want_c)):
-                assert torch.equal(got.indices, want.indices) and torch.equal(got.values, want.values)
-        if Q <= 1100:
-            check_topk(got_u, q, gal, 10, 1e-4, relative=False)
-    finally:
-        lib.irr_debug_set_cluster_size(0)
-
-
 def test_config5_scaled_down_k10_q8192_d2560():
     """BASELINE.json configs[4] (10M x 2560 bf16, Q=8192, k=10 over 8 GPUs) scaled to one eighth of
     one GPU's shard: N = 160,000 rows, the same Q, k, D — the kernel instantiation the full config
