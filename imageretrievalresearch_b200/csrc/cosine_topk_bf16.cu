@@ -66,7 +66,6 @@ struct Knobs {
   bool producers;            // IRR_NORMS_INSIDE=0: no in-kernel norm producers
   int producers_min_pairs;   // IRR_NORMS_MIN_PAIRS: query-tile pairs from which the producers are used
   int norm_ahead;            // IRR_NORM_AHEAD: tiles the producers may run ahead (negative = unpaced)
-  bool shared_norms;         // IRR_NORMS_SHARED=0: global-memory producers instead of shared tile norms
   bool fused_pair;           // IRR_FUSED_PAIR=0: no fused norms in the pair kernel (pre-pass instead)
 };
 const Knobs& knobs() {
@@ -80,7 +79,6 @@ const Knobs& knobs() {
     r.producers = !flag("IRR_NORMS_INSIDE", '0');
     r.producers_min_pairs = num("IRR_NORMS_MIN_PAIRS", 3);
     r.norm_ahead = num("IRR_NORM_AHEAD", 2);
-    r.shared_norms = !flag("IRR_NORMS_SHARED", '0');
     r.fused_pair = !flag("IRR_FUSED_PAIR", '0');
     return r;
   }();
@@ -553,8 +551,6 @@ __device__ __forceinline__ int norm_warp_index(int warp) { return warp < 4 ? war
 constexpr int NORMS_CACHED = 0;      // g_inv_norm (the caller's Gallery cache)
 constexpr int NORMS_PRODUCERS = 1;   // grid-wide in-kernel producers reading global memory (>= 3 pairs)
 constexpr int NORMS_FUSED = 2;       // square-summed from the staged gallery tiles (1-2 pairs)
-constexpr int NORMS_SHARED = 3;      // square-summed from the staged tiles ONCE per tile: the clusters
-                                     // that stream a tile together each do a share and publish it
 constexpr int OCTET = 8;                   // rows a norm warp finishes between two publications
 constexpr int OCTETS_PER_TILE = BLOCK_N / OCTET;
 
@@ -782,8 +778,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 1100 + stage);
           // fused norms: this CTA's norm warps have square-summed the stage's previous contents
-          if (NORMS == NORMS_FUSED || NORMS == NORMS_SHARED)
-            mbar_wait(normdone_bar(stage), phase ^ 1u, 1150 + stage);
+          if (NORMS == NORMS_FUSED) mbar_wait(normdone_bar(stage), phase ^ 1u, 1150 + stage);
           if (lane == 0) {
             const uint32_t a_dst = smem_base + stage * P_STAGE_BYTES;
             const uint32_t b_dst = a_dst + P_A_BYTES;
@@ -877,55 +872,6 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     }
-  } else if (NORMS == NORMS_SHARED && is_norm_warp(warp)) {
-    // ===================== shared gallery norms (a share of every tile, once per tile) ========
-    // The query-tile pairs of a gallery chunk stream the same tiles at the same time on different
-    // clusters.  Each of them square-sums a SHARE of every tile — whole octets of rows of its
-    // CTAs' halves — out of the shared-memory stages its own MMAs just read (no second trip of the
-    // gallery through L2, the arithmetic done once per tile, not once per consumer), writes
-    // 1/max(|g|,eps) to norm_out and counts the octet on the tile's counter; every epilogue waits
-    // for the tile's full count.  Shares go to the units of the chunk that run in the chunk's
-    // FIRST wave (the P0 lowest-numbered ones: units of a chunk are consecutive, clusters take
-    // units in increasing order) — a unit that only runs a wave later finds the norms there, and
-    // nobody ever waits for a unit that has not started.  Octet j of a half belongs to the unit
-    // with j mod P0 == its number in the chunk.
-    const int nt = norm_warp_index(warp) * 32 + lane;      // this thread's row of the CTA's half
-    const int oct = nt >> 3;
-    const bool f16 = is_f16 != 0;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int u = cluster_id; u < total_units; u += num_clusters) {
-      const int chunk = u / m_pairs, mp = u - chunk * m_pairs;
-      const int first_u = chunk * m_pairs;
-      const int p0 = min(m_pairs, (first_u / num_clusters + 1) * num_clusters - first_u);
-      const bool mine = mp < p0 && (oct % p0) == mp;
-      const int t0 = chunk * tiles_per_chunk;
-      const int t1 = min(t0 + tiles_per_chunk, n_tiles);
-      for (int t = t0; t < t1; ++t) {
-        float sa = 0.f, sb = 0.f;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase, 1500 + stage);   // the stage's MMAs have retired
-          if (mine) {
-            const uint4* r = reinterpret_cast<const uint4*>(smem_gen + stage * P_STAGE_BYTES + P_A_BYTES + nt * 128);
-            if (f16) norm_row_sums<true>(r, nt, sa, sb);
-            else     norm_row_sums<false>(r, nt, sa, sb);
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(normdone_bar(stage));   // the producer may refill the stage
-          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
-        }
-        const int row_g = t * BLOCK_N + static_cast<int>(rank) * P_B_ROWS + nt;
-        if (mine && row_g < N) norm_out[row_g] = 1.0f / fmaxf(sqrtf(sa + sb), eps);
-        __syncwarp();
-        if (mine && (lane & 7) == 0) {
-          const int rows = min(OCTET, N - row_g);
-          if (rows > 0) {
-            __threadfence();                                  // the octet's norms before its count
-            atomicAdd(tile_rows_done + t, static_cast<uint32_t>(rows));
-          }
-        }
-      }
-    }
   } else if (NORMS_INSIDE && is_norm_warp(warp)) {
     // ===================== gallery-norm producers (whole grid, need order) =====================
     const int nw = static_cast<int>(blockIdx.x) * 4 + norm_warp_index(warp);
@@ -996,8 +942,8 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
           mbar_wait_cluster(gnfull_bar(as), aphase, 1600 + as);   // both halves' norms have landed
         } else {
           const int c0 = n0 + et, c1 = n0 + et + EPI_THREADS;
-          if (NORMS_INSIDE || NORMS == NORMS_SHARED) {
-            if (NORMS_INSIDE && et == 0) *stream_pos = (u / num_clusters) * tiles_per_chunk + (t - t0);
+          if (NORMS_INSIDE) {
+            if (et == 0) *stream_pos = (u / num_clusters) * tiles_per_chunk + (t - t0);
             // producers publish rows in octets; the tile is usable once all of its rows are counted
             if (lane == 0) {
               const uint32_t need = static_cast<uint32_t>(min(BLOCK_N, N - n0));
@@ -1098,8 +1044,7 @@ bool use_pair(int64_t Q, bool cached_norms) {
 // CTA there: measured 512 queries 1.69 vs 1.66 ms with the pre-pass, 768 queries 2.14 vs 2.54 ms)
 int pair_norm_mode(bool cached, int m_pairs) {
   if (cached) return NORMS_CACHED;
-  if (knobs().producers && m_pairs >= knobs().producers_min_pairs)
-    return knobs().shared_norms ? NORMS_SHARED : NORMS_PRODUCERS;
+  if (knobs().producers && m_pairs >= knobs().producers_min_pairs) return NORMS_PRODUCERS;
   return knobs().fused_pair ? NORMS_FUSED : NORMS_CACHED;   // CACHED here = streaming pre-pass first
 }
 
@@ -1135,7 +1080,7 @@ irr_status launch_pair(const CUtensorMap& tq, const CUtensorMap& tg, const float
   }
   const int num_kb = (D + BLOCK_K - 1) / BLOCK_K;
   const int threads = NORMS != NORMS_CACHED ? P_THREADS_NORM : P_THREADS;
-  if (NORMS == NORMS_PRODUCERS || NORMS == NORMS_SHARED) {
+  if (NORMS == NORMS_PRODUCERS) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.grid);
     cfg.blockDim = dim3(threads);
@@ -1314,8 +1259,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   // one memset: the rows' shared floors and (if used) the per-tile norm counters
   IRR_CUDA_TRY(cudaMemsetAsync(
       row_floor, 0,
-      mode == NORMS_PRODUCERS || mode == NORMS_SHARED
-          ? align_up(static_cast<size_t>(Q) * 4, 256) + static_cast<size_t>(p.n_tiles) * 4
+      mode == NORMS_PRODUCERS ? align_up(static_cast<size_t>(Q) * 4, 256) + static_cast<size_t>(p.n_tiles) * 4
                               : static_cast<size_t>(Q) * 4,
       st));
 
@@ -1334,9 +1278,6 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
     if (mode == NORMS_PRODUCERS) {   // gin_ws is written by the kernel's own norm producers
       if (small_k) IRR_LAUNCH_PAIR(4, NORMS_PRODUCERS, gin_ws); else IRR_LAUNCH_PAIR(16, NORMS_PRODUCERS, gin_ws);
       if (s == IRR_OK && refused) mode = NORMS_CACHED;   // no co-resident grid: pre-pass instead
-    } else if (mode == NORMS_SHARED) {
-      if (small_k) IRR_LAUNCH_PAIR(4, NORMS_SHARED, gin_ws); else IRR_LAUNCH_PAIR(16, NORMS_SHARED, gin_ws);
-      if (s == IRR_OK && refused) mode = NORMS_CACHED;
     } else if (mode == NORMS_FUSED) {
       if (small_k) IRR_LAUNCH_PAIR(4, NORMS_FUSED, nullptr); else IRR_LAUNCH_PAIR(16, NORMS_FUSED, nullptr);
     }
