@@ -203,7 +203,7 @@ struct KParams {
   float *losses, *pair_cos, *row_stats;
   uint4 *dq, *dp, *dn;
   unsigned int* sync_word;
-  float* partials;  // [gridDim.x * groups][4], 16-byte aligned
+  float* partials;  // [gridDim.x][4], 16-byte aligned
   int hints;        // measurement knob IRR_LOSS_HINTS: 1 = evict-first loads, 2 = streaming stores
   int stages;       // ring depth per group (1..MAX_STAGES)
 };
@@ -396,36 +396,39 @@ loss_fwd_bwd_kernel(const KParams P) {
   // before it touches memory, see above)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  // ---- deterministic reduction of the loss scalars: one partial per group (fixed row -> group
-  // map), the last CTA to check in adds them in a fixed order ----
+  // ---- deterministic reduction of the loss scalars ----
+  // group partials (fixed row -> group map) -> one partial per CTA, added in group order by the
+  // CTA's first warp -> the last CTA to check in adds the CTAs' partials in a fixed order.  Only
+  // warp 0 takes part after the barrier; the ticket is ONE acq_rel atomic (its release covers the
+  // partial this warp just wrote, its acquire the other CTAs' partials) instead of two fences
+  // around a relaxed one — this tail runs on a single SM while the other 147 idle.
   constexpr int NL = TRIPLET ? 4 : 1;
-  if (gt == 0)
-    reinterpret_cast<float4*>(P.partials)[gg] = make_float4(lsum[0], lsum[1], lsum[2], lsum[3]);
+  __shared__ float4 cta_part[MAX_GROUPS];
+  if (gt == 0) cta_part[grp] = make_float4(lsum[0], lsum[1], lsum[2], lsum[3]);
   __syncthreads();
-  __shared__ int is_last;
-  __shared__ float4 red[MAX_THREADS / 32];
-  if (threadIdx.x == 0) {
-    __threadfence();   // cumulative: covers the group leaders' partials ordered by the barrier
-    const unsigned int prev = atomicAdd(P.sync_word, 1u);
-    is_last = (prev == gridDim.x - 1);
-    __threadfence();
-  }
-  __syncthreads();
-  if (is_last) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t i = threadIdx.x; i < tg; i += blockDim.x) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(P.partials) + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  if (threadIdx.x < 32) {
+    const int l = threadIdx.x;
+    if (l == 0) {
+      float4 acc = cta_part[0];
+      for (int g = 1; g < groups; ++g) {
+        const float4 v = cta_part[g];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      reinterpret_cast<float4*>(P.partials)[blockIdx.x] = acc;
     }
-    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const int nw = blockDim.x >> 5;
-      float4 v = threadIdx.x < nw ? red[threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
-      v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
-      if (threadIdx.x == 0) {
-        const float r[4] = {v.x, v.y, v.z, v.w};
+    unsigned int prev = 0;
+    if (l == 0)
+      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(P.sync_word) : "memory");
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev == gridDim.x - 1) {       // last CTA: every other CTA's partial is visible
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = l; i < static_cast<int>(gridDim.x); i += 32) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(P.partials) + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+      if (l == 0) {
+        const float r[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
         for (int j = 0; j < NL; ++j) P.losses[j] = r[j] * P.red_scale;
         *P.sync_word = 0u;  // self-reset for the next call on this workspace
