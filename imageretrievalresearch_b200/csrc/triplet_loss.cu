@@ -34,7 +34,8 @@ namespace {
 constexpr int MAX_STAGES = 4;    // rows a group keeps in flight (ring depth, chosen at launch)
 constexpr int MAX_GROUPS = 15;   // groups per CTA: one named barrier each (ids 1..15)
 constexpr int MAX_THREADS = 1024;
-constexpr int SMEM_BUDGET = 220 * 1024;
+constexpr int SMEM_BUDGET = 216 * 1024;   // dynamic; ~5 KB of static shared memory sit next to it
+constexpr int DYN_MAX_ROWS = 256;         // rows per CTA up to which groups take rows on demand
 
 struct Coef {
   float aqq, aqp, aqn, app, ann;
@@ -205,7 +206,8 @@ struct KParams {
   unsigned int* sync_word;
   float* partials;  // [gridDim.x][4], 16-byte aligned
   int hints;        // measurement knob IRR_LOSS_HINTS: 1 = evict-first loads, 2 = streaming stores
-  int stages;       // ring depth per group (1..MAX_STAGES)
+  int stages;       // ring depth per group (2..MAX_STAGES)
+  int dynamic;      // groups take the CTA's rows on demand when the CTA has few of them
 };
 
 template <int KIND, bool TRIPLET, int GW>
@@ -238,12 +240,21 @@ loss_fwd_bwd_kernel(const KParams P) {
   // completed and flushed.  A no-op when the launch does not carry the attribute.
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // Row -> group map: row r belongs to group (r mod tg), numbered group-slot-major ACROSS the CTAs,
-  // so that the rows left over after the last full round (B mod tg of them) go one or two to every
-  // SM instead of all to the first few CTAs (4096 bf16 rows over 148 x 12 groups: 27-28 rows on
-  // every SM instead of 36 on the first 46 and 24 on the rest).  Fixed map: deterministic sums.
-  const int64_t gg = static_cast<int64_t>(grp) * gridDim.x + blockIdx.x;
-  const int64_t tg = static_cast<int64_t>(gridDim.x) * groups;
+  // Rows of this CTA: r_i = blockIdx + i * gridDim, i < cnt (CTA-interleaved, so every SM gets
+  // B / gridDim rows give or take one: 27-28 of 4096 on each of 148 SMs).  Inside the CTA a group
+  // takes item i = grp, grp + groups, ... (static) or — with few rows per CTA, where "three rows
+  // for some groups, two for the others" would cost a fifth of the time — whichever item is next
+  // when one of its ring slots frees up (a shared-memory ticket).  The loss terms of a row taken
+  // on demand go to a per-item slot and are added in item order, so the sums do not depend on
+  // which group happened to take which row: deterministic either way.
+  const int64_t G = gridDim.x;
+  const int cnt = blockIdx.x < P.B ? static_cast<int>((P.B - blockIdx.x + G - 1) / G) : 0;
+  const bool dynamic = P.dynamic && cnt <= DYN_MAX_ROWS;
+  __shared__ int next_item;
+  __shared__ int slot_item[MAX_GROUPS][MAX_STAGES];
+  __shared__ float4 item_loss[DYN_MAX_ROWS];
+  if (threadIdx.x == 0) next_item = groups * stages;
+  int* my_items = slot_item[grp];
 
   auto issue = [&](int64_t row, int s) {
     const uint32_t dst = smem_u32(my_slots + static_cast<size_t>(s) * slot_bytes);
@@ -261,19 +272,31 @@ loss_fwd_bwd_kernel(const KParams P) {
     }
   };
 
-  if (gt == 0) {
-    for (int s = 0; s < stages; ++s) {
-      const int64_t row = gg + s * tg;
-      if (row < P.B) issue(row, s);
+  // a ring slot's phase completes once per round: with a row's bytes, or — no item left — with a
+  // bare arrive; the item number travels in shared memory, ordered by that same barrier
+  auto fill = [&](int item, int s) {
+    if (item < cnt) {
+      my_items[s] = item;
+      issue(blockIdx.x + static_cast<int64_t>(item) * G, s);
+    } else {
+      my_items[s] = -1;
+      mbar_arrive(bar0 + 8u * s);
     }
+  };
+  __syncthreads();   // next_item initialised
+  if (gt == 0) {
+    for (int s = 0; s < stages; ++s) fill(grp + s * groups, s);
   }
 
-  float lsum[4] = {0.f, 0.f, 0.f, 0.f};   // kept by the group's first warp only
+  float lsum[4] = {0.f, 0.f, 0.f, 0.f};   // static assignment: kept by the group's first warp
   constexpr int VH = Vec<KIND>::H;
   int it = 0, s = 0;
   uint32_t parity = 0;
-  for (int64_t row = gg; row < P.B; row += tg, ++it) {
+  for (;; ++it) {
     mbar_wait_parked(bar0 + 8u * s, parity, 500 + s);
+    const int item = my_items[s];
+    if (item < 0) break;
+    const int64_t row = blockIdx.x + static_cast<int64_t>(item) * G;
     const uint4* sq = reinterpret_cast<const uint4*>(my_slots + static_cast<size_t>(s) * slot_bytes);
     const uint4* sp = sq + P.vec_per_row;
     const uint4* sn = sp + P.vec_per_row;
@@ -317,8 +340,8 @@ loss_fwd_bwd_kernel(const KParams P) {
     named_bar_sync(1 + grp, GT);   // the ONE barrier per row
     // every thread of the group is past the previous row: its ring slot can be refilled
     if (gt == 0 && it > 0) {
-      const int64_t next = row + static_cast<int64_t>(stages - 1) * tg;
-      if (next < P.B) issue(next, s == 0 ? stages - 1 : s - 1);
+      const int sp = s == 0 ? stages - 1 : s - 1;
+      fill(dynamic ? atomicAdd(&next_item, 1) : my_items[sp] + stages * groups, sp);
     }
 
     // order of the eight slots = warp_reduce8's value index: qq pp nn qp | qn dp dn -
@@ -344,6 +367,7 @@ loss_fwd_bwd_kernel(const KParams P) {
         for (int j = 0; j < 4; ++j) lsum[j] += o.l[j];
       }
       if (gt == 0) {
+        if (dynamic) item_loss[item] = make_float4(o.l[0], o.l[1], o.l[2], o.l[3]);
         if (P.pair_cos) {
           const float nq = fmaxf(sqrtf(S.qq), P.pair_eps);
           P.pair_cos[row] = S.qp / (nq * fmaxf(sqrtf(S.pp), P.pair_eps));
@@ -408,7 +432,15 @@ loss_fwd_bwd_kernel(const KParams P) {
   __syncthreads();
   if (threadIdx.x < 32) {
     const int l = threadIdx.x;
-    if (l == 0) {
+    if (dynamic) {   // the CTA's rows in item order, whoever processed them
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = l; i < cnt; i += 32) {
+        const float4 v = item_loss[i];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+      if (l == 0) reinterpret_cast<float4*>(P.partials)[blockIdx.x] = acc;
+    } else if (l == 0) {
       float4 acc = cta_part[0];
       for (int g = 1; g < groups; ++g) {
         const float4 v = cta_part[g];
@@ -508,7 +540,7 @@ struct LaunchShape {
 
 // measurement knobs for profiles/ (environment, read once): IRR_LOSS_GW, IRR_LOSS_STAGES,
 // IRR_LOSS_HINTS — not an API
-struct LossKnobs { int gw, stages, hints, pdl; };
+struct LossKnobs { int gw, stages, hints, pdl, dynamic; };
 const LossKnobs& loss_knobs() {
   static const LossKnobs k = []() {
     auto num = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
@@ -516,6 +548,7 @@ const LossKnobs& loss_knobs() {
     r.gw = num("IRR_LOSS_GW", 0);
     r.stages = num("IRR_LOSS_STAGES", 0);
     r.hints = num("IRR_LOSS_HINTS", 1);   // evict-first loads measured +3 % (profiles/r01_notes.md)
+    r.dynamic = num("IRR_LOSS_DYNAMIC", 1);   // rows on demand inside a CTA (see the kernel)
     r.pdl = num("IRR_LOSS_PDL", 1);       // programmatic dependent launch (prologue overlaps the predecessor's tail)
     return r;
   }();
@@ -594,6 +627,7 @@ irr_status loss_fwd_bwd(const LossArgs& a, void* ws, size_t ws_bytes, cudaStream
   P.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
   P.hints = loss_knobs().hints;
   P.stages = sh.stages;
+  P.dynamic = loss_knobs().dynamic;
 
   // the attribute is set to the budget once per instantiation and device, not per call
 #define IRR_LAUNCH_LOSS(BF, TR, GWV)                                                              \
