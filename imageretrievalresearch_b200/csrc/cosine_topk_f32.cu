@@ -18,21 +18,20 @@ namespace {
 
 constexpr int BM = 64, BN = 128, BK = 16;
 constexpr int THREADS = 256;
-constexpr int A_LD = BM + 4;
+constexpr int A_LD = BM + 4, B_LD = BN + 4, S_LD = BN + 1;
 constexpr int SMEM_A = 2 * BK * A_LD * 4;
-// gallery-tile width BNT: 128, or 64 for searches with too few 128-row tiles to occupy the SMs
-// (configs[1]: 10k rows = 79 tiles on 148 SMs)
-template <int BNT>
-constexpr int small_smem_bytes() { return SMEM_A + 2 * BK * (BNT + 4) * 4 + BM * (BNT + 1) * 4; }
+constexpr int SMEM_B = 2 * BK * B_LD * 4;
+constexpr int SMEM_S = BM * S_LD * 4;
+constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_S;
 
 struct Plan {
   int m_tiles, n_tiles, tiles_per_chunk, n_chunks;
 };
 
-Plan make_plan(int64_t Q, int64_t N, int bn = BN) {
+Plan make_plan(int64_t Q, int64_t N) {
   Plan p;
   p.m_tiles = static_cast<int>((Q + BM - 1) / BM);
-  p.n_tiles = static_cast<int>((N + bn - 1) / bn);
+  p.n_tiles = static_cast<int>((N + BN - 1) / BN);
   if (p.m_tiles < 1) p.m_tiles = 1;
   if (p.n_tiles < 1) p.n_tiles = 1;
   const int slots = num_sms() * 2;  // two resident CTAs per SM
@@ -52,16 +51,13 @@ Plan make_plan(int64_t Q, int64_t N, int bn = BN) {
 
 // WRITE_SCORES: instead of selecting, publish the dense cosine tile (both norms applied) — the
 // first stage of the large-k path (topk_select.cu).
-template <int KMAX, bool WRITE_SCORES, int BNT>
+template <int KMAX, bool WRITE_SCORES>
 __global__ void __launch_bounds__(THREADS, 2)
 cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
                        const float* __restrict__ g_inv_norm, int Q, int N, int D, int k,
                        int m_tiles, int n_tiles, int tiles_per_chunk,
                        float* __restrict__ part_val, int32_t* __restrict__ part_idx,
                        const float* __restrict__ q_inv_norm, float* __restrict__ scores_out) {
-  constexpr int NB = BNT / 64;          // 64-column halves of the tile: micro-tile 4 x (4*NB)
-  constexpr int B_LD = BNT + 4, S_LD = BNT + 1;
-  constexpr int SMEM_B = 2 * BK * B_LD * 4;
   extern __shared__ __align__(16) uint8_t smem[];
   float* As = reinterpret_cast<float*>(smem);                      // [2][BK][A_LD]
   float* Bs = reinterpret_cast<float*>(smem + SMEM_A);             // [2][BK][B_LD]
@@ -73,7 +69,7 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
   const int m0 = mt * BM;
   const int t0 = chunk * tiles_per_chunk, t1 = min(t0 + tiles_per_chunk, n_tiles);
 
-  // global -> smem staging assignment: A: one float4 / thread, B: NB float4 / thread
+  // global -> smem staging assignment: A: one float4 / thread, B: two float4 / thread
   const int a_row = t >> 2, a_kq = (t & 3) * 4;
   const bool a_ok = m0 + a_row < Q;
   const float* a_src = q + static_cast<size_t>(a_ok ? m0 + a_row : 0) * D + a_kq;
@@ -83,29 +79,29 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
 
   const int num_ks = (D + BK - 1) / BK;
   for (int tile = t0; tile < t1; ++tile) {
-    const int n0 = tile * BNT;
-    const float* b_src[NB];
-    bool b_ok[NB];
+    const int n0 = tile * BN;
+    const float* b_src[2];
+    bool b_ok[2];
 #pragma unroll
-    for (int i = 0; i < NB; ++i) {
+    for (int i = 0; i < 2; ++i) {
       const int f = t + i * THREADS;
       const int row = f >> 2;
       b_ok[i] = n0 + row < N;
       b_src[i] = g + static_cast<size_t>(b_ok[i] ? n0 + row : 0) * D + (f & 3) * 4;
     }
-    float acc[4][4 * NB];
+    float acc[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4 * NB; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-    float4 ra, rb[NB];
+    float4 ra, rb[2];
     auto gload = [&](int ks) {
       const int kk = ks * BK;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       ra = (a_ok && kk + a_kq < D) ? __ldg(reinterpret_cast<const float4*>(a_src + kk)) : z;
 #pragma unroll
-      for (int i = 0; i < NB; ++i) {
+      for (int i = 0; i < 2; ++i) {
         const int kq = ((t + i * THREADS) & 3) * 4;
         rb[i] = (b_ok[i] && kk + kq < D) ? __ldg(reinterpret_cast<const float4*>(b_src[i] + kk)) : z;
       }
@@ -118,7 +114,7 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
       a[(a_kq + 3) * A_LD + a_row] = ra.w;
       float* b = Bs + buf * BK * B_LD;
 #pragma unroll
-      for (int i = 0; i < NB; ++i) {
+      for (int i = 0; i < 2; ++i) {
         const int f = t + i * THREADS;
         const int row = f >> 2, kq = (f & 3) * 4;
         b[(kq + 0) * B_LD + row] = rb[i].x;
@@ -140,17 +136,14 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
 #pragma unroll
       for (int kk = 0; kk < BK; ++kk) {
         const float4 av = *reinterpret_cast<const float4*>(a + kk * A_LD);
+        const float4 b0 = *reinterpret_cast<const float4*>(b + kk * B_LD);
+        const float4 b1 = *reinterpret_cast<const float4*>(b + kk * B_LD + 64);
         const float ar[4] = {av.x, av.y, av.z, av.w};
-        float br[4 * NB];
-#pragma unroll
-        for (int h = 0; h < NB; ++h) {
-          const float4 bv = *reinterpret_cast<const float4*>(b + kk * B_LD + 64 * h);
-          br[4 * h + 0] = bv.x; br[4 * h + 1] = bv.y; br[4 * h + 2] = bv.z; br[4 * h + 3] = bv.w;
-        }
+        const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4 * NB; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
       }
       if (ks + 1 < num_ks) {
         sstore(buf ^ 1);  // the other buffer was last read one iteration ago, before the sync below
@@ -158,29 +151,29 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
       }
     }
     // scale by the inverse gallery norms and publish the tile
-    float gn[4 * NB];
+    float gn[8];
 #pragma unroll
-    for (int j = 0; j < 4 * NB; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const int c = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       gn[j] = c < N ? __ldg(g_inv_norm + c) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4 * NB; ++j) {
+      for (int j = 0; j < 8; ++j) {
         const int c = j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4);
         Ss[(ty * 4 + i) * S_LD + c] = acc[i][j] * gn[j];
       }
     __syncthreads();
     if (WRITE_SCORES) {
-      for (int e = t; e < BM * BNT; e += THREADS) {
-        const int r = e / BNT, c = e - r * BNT;
+      for (int e = t; e < BM * BN; e += THREADS) {
+        const int r = e / BN, c = e - r * BN;
         if (m0 + r < Q && n0 + c < N)
           scores_out[static_cast<size_t>(m0 + r) * N + n0 + c] =
               Ss[r * S_LD + c] * __ldg(q_inv_norm + m0 + r);
       }
     } else if (t < BM) {
-      const int n_valid = min(BNT, N - n0);
+      const int n_valid = min(BN, N - n0);
       const float* s = Ss + t * S_LD;
       for (int c = 0; c < n_valid; ++c) top.push_ordered(s[c], n0 + c);
     }
@@ -418,14 +411,8 @@ bool use_big(int64_t Q) {
 
 }  // namespace
 
-// narrow (64-row) gallery tiles when 128-row tiles would leave SMs without a CTA
-int small_tile_width(int64_t Q, int64_t N) {
-  const long long units = ((Q + BM - 1) / BM) * ((N + BN - 1) / BN);
-  return units < num_sms() ? 64 : BN;
-}
-
 size_t f32_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
-  const Plan p = use_big(Q) ? make_plan_big(Q, N) : make_plan(Q, N, small_tile_width(Q, N));
+  const Plan p = use_big(Q) ? make_plan_big(Q, N) : make_plan(Q, N);
   const size_t parts = static_cast<size_t>(p.n_chunks) * Q * k;
   return align_up(static_cast<size_t>(N) * 4, 256) + align_up(parts * 4, 256) * 2 + 256;
 }
@@ -437,8 +424,7 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
   if (N > 0x7fffff00ll || Q > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
   if (ws_bytes < f32_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
   const bool big = use_big(Q);
-  const int bnt = small_tile_width(Q, N);
-  const Plan p = big ? make_plan_big(Q, N) : make_plan(Q, N, bnt);
+  const Plan p = big ? make_plan_big(Q, N) : make_plan(Q, N);
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* gin_ws = reinterpret_cast<float*>(w);
   w += align_up(static_cast<size_t>(N) * 4, 256);
@@ -468,20 +454,20 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
   } while (0)
     if (k <= 4) IRR_LAUNCH_BIG(4); else IRR_LAUNCH_BIG(16);
 #undef IRR_LAUNCH_BIG
+  } else if (k <= 4) {
+    auto kern = cosine_topk_f32_kernel<4, false>;
+    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(static_cast<const float*>(q), static_cast<const float*>(g),
+                                            gin, static_cast<int>(Q), static_cast<int>(N), D, k,
+                                            p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi,
+                                            nullptr, nullptr);
   } else {
-#define IRR_LAUNCH_SMALL(KM, BNTV)                                                                \
-  do {                                                                                            \
-    auto kern = cosine_topk_f32_kernel<KM, false, BNTV>;                                          \
-    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                      small_smem_bytes<BNTV>()));                                 \
-    kern<<<grid, THREADS, small_smem_bytes<BNTV>(), st>>>(                                        \
-        static_cast<const float*>(q), static_cast<const float*>(g), gin, static_cast<int>(Q),     \
-        static_cast<int>(N), D, k, p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi, nullptr,      \
-        nullptr);                                                                                 \
-  } while (0)
-    if (bnt == 64) { if (k <= 4) IRR_LAUNCH_SMALL(4, 64); else IRR_LAUNCH_SMALL(16, 64); }
-    else           { if (k <= 4) IRR_LAUNCH_SMALL(4, 128); else IRR_LAUNCH_SMALL(16, 128); }
-#undef IRR_LAUNCH_SMALL
+    auto kern = cosine_topk_f32_kernel<16, false>;
+    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(static_cast<const float*>(q), static_cast<const float*>(g),
+                                            gin, static_cast<int>(Q), static_cast<int>(N), D, k,
+                                            p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi,
+                                            nullptr, nullptr);
   }
   profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
@@ -505,10 +491,9 @@ irr_status f32_cosine_scores(const void* q, const void* g, const float* g_inv_no
     return IRR_OK;
   }
   const Plan p = make_plan(Q, N);
-  auto kern = cosine_topk_f32_kernel<4, true, BN>;
-  IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    small_smem_bytes<BN>()));
-  kern<<<p.m_tiles * p.n_chunks, THREADS, small_smem_bytes<BN>(), st>>>(
+  auto kern = cosine_topk_f32_kernel<4, true>;
+  IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  kern<<<p.m_tiles * p.n_chunks, THREADS, SMEM_BYTES, st>>>(
       static_cast<const float*>(q), static_cast<const float*>(g), g_inv_norm, static_cast<int>(Q),
       static_cast<int>(N), D, 1, p.m_tiles, p.n_tiles, p.tiles_per_chunk, nullptr, nullptr,
       q_inv_norm, out_scores);
