@@ -51,7 +51,15 @@ Plan make_plan(int64_t Q, int64_t N) {
 
 // WRITE_SCORES: instead of selecting, publish the dense cosine tile (both norms applied) — the
 // first stage of the large-k path (topk_select.cu).
-template <int KMAX, bool WRITE_SCORES>
+//
+// Every dot product is summed as (first half of K) + (second half of K), each half in ascending k.
+// SPLIT = 1: one CTA runs both halves (the first half's partial tile waits in its score buffer).
+// SPLIT = 2: a cluster of two CTAs runs one half each and the second CTA hands its partial tile to
+// the first through distributed shared memory — for searches with too few gallery tiles to give
+// every SM a CTA (configs[1]: 10k rows = 79 tiles on 148 SMs).  Same additions in the same order,
+// so the two variants return identical bits and a gallery scanned in blocks (StreamedGallery)
+// ranks exactly like the resident one whichever variant each block size selects.
+template <int KMAX, bool WRITE_SCORES, int SPLIT>
 __global__ void __launch_bounds__(THREADS, 2)
 cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
                        const float* __restrict__ g_inv_norm, int Q, int N, int D, int k,
@@ -65,7 +73,9 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
 
   const int t = threadIdx.x;
   const int ty = t >> 4, tx = t & 15;
-  const int chunk = blockIdx.x / m_tiles, mt = blockIdx.x - chunk * m_tiles;
+  const int unit = blockIdx.x / SPLIT;
+  const uint32_t rank = SPLIT == 2 ? cluster_ctarank() : 0u;   // which half of K this CTA sums
+  const int chunk = unit / m_tiles, mt = unit - chunk * m_tiles;
   const int m0 = mt * BM;
   const int t0 = chunk * tiles_per_chunk, t1 = min(t0 + tiles_per_chunk, n_tiles);
 
@@ -78,8 +88,12 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
   top.reset();
 
   const int num_ks = (D + BK - 1) / BK;
+  const int half_ks = (num_ks + 1) / 2;
   for (int tile = t0; tile < t1; ++tile) {
     const int n0 = tile * BN;
+    // SPLIT == 2: the first CTA is done with the previous tile's score buffer before the second
+    // one writes this tile's partial into it
+    if (SPLIT == 2) cluster_sync_all();
     const float* b_src[2];
     bool b_ok[2];
 #pragma unroll
@@ -124,31 +138,66 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
       }
     };
 
-    gload(0);
-    __syncthreads();  // previous tile's readers of As/Bs/Ss are done
-    sstore(0);
-    __syncthreads();
-    for (int ks = 0; ks < num_ks; ++ks) {
-      const int buf = ks & 1;
-      if (ks + 1 < num_ks) gload(ks + 1);
-      const float* a = As + buf * BK * A_LD + ty * 4;
-      const float* b = Bs + buf * BK * B_LD + tx * 4;
+    // K-slabs [ks0, ks1) into acc (ascending k; slab ks sits in buffer (ks - ks0) & 1)
+    auto run_k = [&](int ks0, int ks1) {
+      if (ks0 >= ks1) return;
+      gload(ks0);
+      __syncthreads();  // previous readers of As/Bs (and of the previous tile's Ss) are done
+      sstore(0);
+      __syncthreads();
+      for (int ks = ks0; ks < ks1; ++ks) {
+        const int buf = (ks - ks0) & 1;
+        if (ks + 1 < ks1) gload(ks + 1);
+        const float* a = As + buf * BK * A_LD + ty * 4;
+        const float* b = Bs + buf * BK * B_LD + tx * 4;
 #pragma unroll
-      for (int kk = 0; kk < BK; ++kk) {
-        const float4 av = *reinterpret_cast<const float4*>(a + kk * A_LD);
-        const float4 b0 = *reinterpret_cast<const float4*>(b + kk * B_LD);
-        const float4 b1 = *reinterpret_cast<const float4*>(b + kk * B_LD + 64);
-        const float ar[4] = {av.x, av.y, av.z, av.w};
-        const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        for (int kk = 0; kk < BK; ++kk) {
+          const float4 av = *reinterpret_cast<const float4*>(a + kk * A_LD);
+          const float4 b0 = *reinterpret_cast<const float4*>(b + kk * B_LD);
+          const float4 b1 = *reinterpret_cast<const float4*>(b + kk * B_LD + 64);
+          const float ar[4] = {av.x, av.y, av.z, av.w};
+          const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        if (ks + 1 < ks1) {
+          sstore(buf ^ 1);  // the other buffer was last read one iteration ago, before the sync below
+          __syncthreads();
+        }
+      }
+    };
+    // this thread's 4 x 8 elements of the score buffer (private to the thread: no barrier needed
+    // between its own store and load)
+    auto s_at = [&](int i, int j) -> float* {
+      return Ss + (ty * 4 + i) * S_LD + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+    };
+    if (SPLIT == 1) {
+      run_k(0, half_ks);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { *s_at(i, j) = acc[i][j]; acc[i][j] = 0.f; }
+      run_k(half_ks, num_ks);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = *s_at(i, j) + acc[i][j];      // first half + second half
+    } else {
+      if (rank == 0) run_k(0, half_ks); else run_k(half_ks, num_ks);
+      if (rank == 1) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+          for (int j = 0; j < 8; ++j) st_shared_cluster_f32(mapa_rank(smem_u32(s_at(i, j)), 0), acc[i][j]);
       }
-      if (ks + 1 < num_ks) {
-        sstore(buf ^ 1);  // the other buffer was last read one iteration ago, before the sync below
-        __syncthreads();
-      }
+      cluster_sync_all();   // the second half's partial tile has landed in the first CTA
+      if (rank == 1) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = acc[i][j] + *s_at(i, j);      // first half + second half
     }
     // scale by the inverse gallery norms and publish the tile
     float gn[8];
@@ -178,7 +227,7 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
       for (int c = 0; c < n_valid; ++c) top.push_ordered(s[c], n0 + c);
     }
   }
-  if (!WRITE_SCORES && t < BM && m0 + t < Q) {
+  if (!WRITE_SCORES && rank == 0 && t < BM && m0 + t < Q) {
     const size_t o = (static_cast<size_t>(chunk) * Q + m0 + t) * k;
 #pragma unroll
     for (int j = 0; j < KMAX; ++j)
@@ -187,6 +236,7 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
         part_idx[o + j] = top.i[j];
       }
   }
+  // (SPLIT == 2: every DSMEM store precedes the last cluster barrier, so either CTA may exit now)
 }
 
 
@@ -401,6 +451,15 @@ cosine_topk_f32_big_kernel(const float* __restrict__ q, const float* __restrict_
 }
 
 // IRR_F32_SMALL_TILES=1 forces the 64 x 128 kernel (measurement / bit-equality knob, not an API)
+// IRR_F32_SPLITK=0: never split K over a CTA pair (measurement knob, not an API)
+bool split_k_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("IRR_F32_SPLITK");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 bool use_big(int64_t Q) {
   static const bool forced_small = []() {
     const char* e = getenv("IRR_F32_SMALL_TILES");
@@ -454,20 +513,35 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
   } while (0)
     if (k <= 4) IRR_LAUNCH_BIG(4); else IRR_LAUNCH_BIG(16);
 #undef IRR_LAUNCH_BIG
-  } else if (k <= 4) {
-    auto kern = cosine_topk_f32_kernel<4, false>;
-    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(static_cast<const float*>(q), static_cast<const float*>(g),
-                                            gin, static_cast<int>(Q), static_cast<int>(N), D, k,
-                                            p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi,
-                                            nullptr, nullptr);
   } else {
-    auto kern = cosine_topk_f32_kernel<16, false>;
-    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(static_cast<const float*>(q), static_cast<const float*>(g),
-                                            gin, static_cast<int>(Q), static_cast<int>(N), D, k,
-                                            p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi,
-                                            nullptr, nullptr);
+    // too few CTAs to give every SM one: split K over a cluster of two CTAs (same bits, see the kernel)
+    const bool split = grid <= num_sms() && split_k_enabled();
+#define IRR_LAUNCH_SMALL(KM, SP)                                                                  \
+  do {                                                                                            \
+    auto kern = cosine_topk_f32_kernel<KM, false, SP>;                                            \
+    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+    cudaLaunchConfig_t cfg = {};                                                                  \
+    cfg.gridDim = dim3(grid * SP);                                                                \
+    cfg.blockDim = dim3(THREADS);                                                                 \
+    cfg.dynamicSmemBytes = SMEM_BYTES;                                                            \
+    cfg.stream = st;                                                                              \
+    cudaLaunchAttribute at[1];                                                                    \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                               \
+    at[0].val.clusterDim.x = SP;                                                                  \
+    at[0].val.clusterDim.y = 1;                                                                   \
+    at[0].val.clusterDim.z = 1;                                                                   \
+    cfg.attrs = at;                                                                               \
+    cfg.numAttrs = SP == 2 ? 1 : 0;                                                               \
+    IRR_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, static_cast<const float*>(q),                     \
+                                    static_cast<const float*>(g), gin, static_cast<int>(Q),       \
+                                    static_cast<int>(N), static_cast<int>(D), static_cast<int>(k),\
+                                    p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi,              \
+                                    static_cast<const float*>(nullptr),                           \
+                                    static_cast<float*>(nullptr)));                               \
+  } while (0)
+    if (split) { if (k <= 4) IRR_LAUNCH_SMALL(4, 2); else IRR_LAUNCH_SMALL(16, 2); }
+    else       { if (k <= 4) IRR_LAUNCH_SMALL(4, 1); else IRR_LAUNCH_SMALL(16, 1); }
+#undef IRR_LAUNCH_SMALL
   }
   profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
@@ -491,7 +565,7 @@ irr_status f32_cosine_scores(const void* q, const void* g, const float* g_inv_no
     return IRR_OK;
   }
   const Plan p = make_plan(Q, N);
-  auto kern = cosine_topk_f32_kernel<4, true>;
+  auto kern = cosine_topk_f32_kernel<4, true, 1>;
   IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   kern<<<p.m_tiles * p.n_chunks, THREADS, SMEM_BYTES, st>>>(
       static_cast<const float*>(q), static_cast<const float*>(g), g_inv_norm, static_cast<int>(Q),

@@ -116,6 +116,28 @@ def test_config_fp32_10k_exactness():
     check_topk(irr.cosine_topk(q2.cuda(), gal2.cuda(), 3), q2, gal2, 3, FP32_REL, relative=True)
 
 
+@pytest.mark.parametrize("D", [1536, 72, 16])
+def test_fp32_split_k_pair_returns_the_single_cta_bits(D):
+    """fp32, up to 64 queries: with too few gallery tiles to occupy the SMs the K dimension is split
+    over a cluster of two CTAs (the second hands its partial tile over through distributed shared
+    memory); with many tiles one CTA sums both halves.  Same additions in the same order — so a
+    gallery searched in shards small enough for the split path merges to exactly the unsharded
+    result (D = 72: five K-slabs, uneven halves; D = 16: the second half is empty)."""
+    N, Q, k = 30_000, 64, 3
+    q, gal = synthetic.tied_gallery(N, D, Q, seed=D)
+    qd, gd = q.cuda(), gal.cuda()
+    whole = irr.cosine_topk(qd, gd, k)                       # 235 tiles: one CTA per tile
+    check_topk(whole, q, gal, k, FP32_REL, relative=True)
+    cv, ci = [], []
+    for r in range(4):                                       # 59 tiles each: CTA pairs
+        lo, hi = irr.shard_bounds(N, 4, r)
+        part = irr.cosine_topk(qd, gd[lo:hi], k, idx_offset=lo)
+        cv.append(part.values)
+        ci.append(part.indices)
+    mv, mi = _ops.topk_merge(torch.stack(cv), torch.stack(ci))
+    assert torch.equal(mi, whole.indices) and torch.equal(mv, whole.values)
+
+
 # -------------------------------------------------------------------------------------------------
 # BASELINE.json configs[2]: fused losses fwd/bwd on 4096 x 1536 triplets, margins 0.2/0.3/0.5
 # -------------------------------------------------------------------------------------------------
