@@ -6,10 +6,13 @@ wrapper raises on a non-zero irr_status.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libirr_b200.so"
+# IRR_B200_LIB: load another build of the same library (A/B measurements of two builds in one
+# session — profiles/); not an API
+LIB_PATH = Path(os.environ["IRR_B200_LIB"]) if os.environ.get("IRR_B200_LIB") else _PKG / "libirr_b200.so"
 
 IRR_F32, IRR_BF16, IRR_F16 = 0, 1, 2
 IRR_MAX_K = 256

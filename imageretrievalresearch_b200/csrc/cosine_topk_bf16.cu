@@ -576,7 +576,7 @@ static __device__ __noinline__ void wait_tile_norms_slow(const uint32_t* cnt, ui
              ld_acquire_gpu(cnt), need);
       __trap();
     }
-    __nanosleep(100);
+    __nanosleep(500);
   }
 }
 
@@ -903,7 +903,10 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
       if (tile >= n_tiles) continue;
       if (paced) {
         const int key = w * tiles_per_chunk + j;
-        while (key > *stream_pos + norm_ahead) __nanosleep(256);
+        // a tile takes ~10 us of MMAs whatever the batch size: polling the position every ~1.5 us
+        // keeps the two-tile lead (at 256 ns this loop alone was a third of the kernel's executed
+        // instructions: 123 k polls per warp and launch)
+        while (key > *stream_pos + norm_ahead) __nanosleep(1500);
       }
       const int row0 = tile * BLOCK_N + oct * OCTET;
       if (row0 >= N) continue;
