@@ -308,9 +308,22 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_cluster_suspend(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 static __device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity, int tag) {
   const uint64_t t0 = global_timer_ns();
-  while (!mbar_try_wait_cluster(bar, parity)) {
+  while (!mbar_try_wait_cluster_suspend(bar, parity, 4000u)) {
     if (global_timer_ns() - t0 > 4000000000ull) {
       printf("irr_b200: mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, tag, parity);
