@@ -376,6 +376,15 @@ def extra_configs(irr, a, queries, shard, peaks, search):
                       "hbm_frac_of_step": b / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                       "algorithmic_bytes": b})
     out["sweep"] = sweep
+    # the same Q as the headline against a Gallery handle (inverse norms cached once, as a resident
+    # index would hold them): what recomputing the norms inside the kernel every step costs
+    handle = irr.Gallery(shard)
+    ms = event_ms(lambda: handle.search(queries, k), a.steps, warm=a.warmup)
+    Q = queries.shape[0]
+    out["cached_norms"] = {"Q": Q, "ms_per_step": ms, "queries_per_s": Q / (ms * 1e-3),
+                           "tensor_frac_of_step": 2.0 * Q * n_local * D / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                           "what": "headline search through irr.Gallery (1/max(|g|,eps) cached at construction)"}
+    del handle
     # configs[2]: fused contrastive + cosine-embedding losses fwd+bwd, 4096 x 1536 triplets.
     # 151 MB (fp32) per call is about the size of L2: rotate over 6 input sets (> 2x L2).
     B, LD = 4096, 1536

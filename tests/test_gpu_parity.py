@@ -289,6 +289,30 @@ def test_ragged_shapes(dtype, Q, N, D, k):
     assert (res.values[:, :-1] >= res.values[:, 1:]).all()
 
 
+def test_random_shapes_against_the_oracle():
+    """Seeded random (Q, N, D, k, dtype, cached) draws — ragged everything, duplicated rows — against
+    the fp64 oracle: the shapes nobody thought of."""
+    import random
+    rng = random.Random(20261018)
+    for case in range(28):
+        dtype = rng.choice([torch.bfloat16, torch.bfloat16, torch.float32])
+        Q = rng.choice([1, 2, 7, 63, 64, 65, 127, 130, 255, 260, 383, 390, 511, 520, 700, 1025])
+        N = rng.randint(3, 9000)
+        D = 8 * rng.randint(1, 40) if dtype == torch.bfloat16 else 4 * rng.randint(1, 80)
+        k = min(rng.choice([1, 2, 3, 4, 5, 10, 16, 17, 40]), N)
+        if dtype == torch.float32 and Q > 300:
+            Q = Q // 4 + 1                              # keep the FFMA path's share of the time small
+        q, gal = synthetic.tied_gallery(N, D, Q, seed=1000 + case, dtype=dtype)
+        qd, gd = q.cuda(), gal.cuda()
+        res = irr.Gallery(gd).search(qd, k) if rng.random() < 0.5 else irr.cosine_topk(qd, gd, k)
+        tol, relative = (2e-6, False) if dtype == torch.float32 else (1e-4, False)
+        try:
+            check_topk(res, q, gal, k, tol, relative)
+        except AssertionError as e:
+            raise AssertionError(f"case {case}: Q={Q} N={N} D={D} k={k} {dtype}: {e}") from e
+        assert (res.values[:, :-1] >= res.values[:, 1:]).all()
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_ties_resolve_to_lower_index(dtype):
     q, gal = synthetic.tied_gallery(3000, 64, 40, seed=7, dtype=dtype)
