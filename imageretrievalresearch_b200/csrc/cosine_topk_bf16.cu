@@ -50,7 +50,6 @@ constexpr int SMEM_GN = ACC_STAGES * BLOCK_N * 4;                // inverse gall
 
 struct Plan {
   int m_tiles, n_tiles, tiles_per_chunk, n_chunks, grid;
-  int bn;   // gallery rows per tile (UMMA N): 256, or 128 for small single-tile searches
 };
 
 // The two tensor maps of a query batch (see encode_queries)
@@ -68,7 +67,6 @@ struct Knobs {
   int producers_min_pairs;   // IRR_NORMS_MIN_PAIRS: query-tile pairs from which the producers are used
   int norm_ahead;            // IRR_NORM_AHEAD: tiles the producers may run ahead (negative = unpaced)
   bool fused_pair;           // IRR_FUSED_PAIR=0: no fused norms in the pair kernel (pre-pass instead)
-  bool narrow_tiles;         // IRR_NARROW_TILES=0: never 128-row gallery tiles in the single-CTA kernel
 };
 const Knobs& knobs() {
   static const Knobs k = []() {
@@ -82,27 +80,20 @@ const Knobs& knobs() {
     r.producers_min_pairs = num("IRR_NORMS_MIN_PAIRS", 3);
     r.norm_ahead = num("IRR_NORM_AHEAD", 2);
     r.fused_pair = !flag("IRR_FUSED_PAIR", '0');
-    r.narrow_tiles = !flag("IRR_NARROW_TILES", '0');
     return r;
   }();
   return k;
 }
 
 // Chunk the gallery tiles so that (query tiles x chunks) spreads evenly over the SMs.
-// A single query tile over a small gallery (a shard of a sharded gallery: 125 k rows = 489 tiles on
-// 148 SMs, so the busiest SM does 4 tiles where 3.3 would be its share) may use 128-row gallery
-// tiles instead: the same plan in half-tile units (7 half tiles = 3.5).  HBM-bound either way, so
-// the narrower MMA costs nothing.
-Plan make_plan_bn(int64_t Q, int64_t N, int bn, double* cost_out) {
+Plan make_plan(int64_t Q, int64_t N) {
   Plan p;
   const int sms = num_sms();
-  p.bn = bn;
   p.m_tiles = static_cast<int>((Q + BLOCK_M - 1) / BLOCK_M);
-  p.n_tiles = static_cast<int>((N + bn - 1) / bn);
+  p.n_tiles = static_cast<int>((N + BLOCK_N - 1) / BLOCK_N);
   if (p.m_tiles < 1) p.m_tiles = 1;
   if (p.n_tiles < 1) p.n_tiles = 1;
   // candidates: enough chunks that every SM gets work, few enough that partial lists stay small
-  const double tile_cost = bn == BLOCK_N ? 1.0 : 0.52;
   int best_tpc = 1;
   double best_cost = 1e300;
   const int max_tpc = p.n_tiles < 64 ? p.n_tiles : 64;
@@ -111,7 +102,7 @@ Plan make_plan_bn(int64_t Q, int64_t N, int bn, double* cost_out) {
     const long long units = 1ll * chunks * p.m_tiles;
     const long long waves = (units + sms - 1) / sms;
     // time ~ waves * tpc tiles (+ a per-unit start-up worth roughly a third of a tile)
-    const double cost = static_cast<double>(waves) * (tpc * tile_cost + 0.35);
+    const double cost = static_cast<double>(waves) * (tpc + 0.35);
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best_tpc = tpc;
@@ -123,15 +114,7 @@ Plan make_plan_bn(int64_t Q, int64_t N, int bn, double* cost_out) {
   p.n_chunks = (p.n_tiles + best_tpc - 1) / best_tpc;
   const long long units = 1ll * p.n_chunks * p.m_tiles;
   p.grid = static_cast<int>(units < sms ? units : sms);
-  if (cost_out) *cost_out = best_cost;
   return p;
-}
-Plan make_plan(int64_t Q, int64_t N, bool allow_narrow = false) {
-  double c256 = 0, c128 = 0;
-  const Plan p256 = make_plan_bn(Q, N, BLOCK_N, &c256);
-  if (!allow_narrow || Q > BLOCK_M || !knobs().narrow_tiles) return p256;
-  const Plan p128 = make_plan_bn(Q, N, BLOCK_N / 2, &c128);
-  return c128 < 0.95 * c256 ? p128 : p256;
 }
 
 // One accumulator tile (this thread = one query row, 256 gallery columns): TMEM -> registers 32
@@ -186,10 +169,9 @@ template <int KMAX, bool WRITE_SCORES>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, int n0, int n_valid,
                                               int row, int Q, int N, float qn,
                                               float* __restrict__ scores_out,
-                                              TopKList<KMAX, int32_t>& top, float floor,
-                                              int n_cols = BLOCK_N) {
+                                              TopKList<KMAX, int32_t>& top, float floor) {
 #pragma unroll 1
-  for (int c = 0; c < n_cols; c += 32) {
+  for (int c = 0; c < BLOCK_N; c += 32) {
     float v[32];
     tmem_ld_32x32(taddr + c, v);
     tmem_ld_wait();
@@ -316,7 +298,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         int tiles_per_chunk, int n_chunks, float* __restrict__ part_val,
                         int32_t* __restrict__ part_idx, float* __restrict__ scores_out,
                         uint64_t g_policy, float eps, int tail_tile, int tail_bytes,
-                        uint32_t* __restrict__ row_floor, int is_f16, int bn) {
+                        uint32_t* __restrict__ row_floor, int is_f16) {
   using G = SC;
   constexpr int STAGES = G::STAGES;
   constexpr int ACC = G::ACC;
@@ -385,10 +367,10 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
             const uint32_t b_dst = a_dst + G::A_BYTES;
             const bool tail = mt == tail_tile;
-            mbar_arrive_expect_tx(full_bar(stage), (tail ? tail_bytes : G::A_BYTES) + bn * (BLOCK_K * 2));
+            mbar_arrive_expect_tx(full_bar(stage), (tail ? tail_bytes : G::A_BYTES) + B_STAGE_BYTES);
             tma_load_2d(a_dst, tail ? &tmap_q_tail : &tmap_q, kb * BLOCK_K, mt * BLOCK_M,
                         full_bar(stage), kPolicyEvictLast);
-            tma_load_2d(b_dst, &tmap_g, kb * BLOCK_K, t * bn, full_bar(stage), g_policy);
+            tma_load_2d(b_dst, &tmap_g, kb * BLOCK_K, t * BLOCK_N, full_bar(stage), g_policy);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -397,7 +379,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_16(BLOCK_M, bn, is_f16 != 0);
+    const uint32_t idesc = umma_idesc_16(BLOCK_M, BLOCK_N, is_f16 != 0);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t it = 0;  // accumulator tiles issued by this CTA
@@ -456,9 +438,8 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint4* r1 = reinterpret_cast<const uint4*>(b + (nt + NORM_THREADS) * 128);
           // one branch per stage, not one select per element: these four warps have to keep pace
           // with the HBM stream
-          // (128-row tiles: the stage's second half holds nothing; its sums are never read)
-          if (is_f16) norm_stage_sums<true>(r0, bn == BLOCK_N ? r1 : r0, nt, s0a, s0b, s1a, s1b);
-          else        norm_stage_sums<false>(r0, bn == BLOCK_N ? r1 : r0, nt, s0a, s0b, s1a, s1b);
+          if (is_f16) norm_stage_sums<true>(r0, r1, nt, s0a, s0b, s1a, s1b);
+          else        norm_stage_sums<false>(r0, r1, nt, s0a, s0b, s1a, s1b);
           __syncwarp();
           if (lane == 0) mbar_arrive(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -494,7 +475,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
       if (WRITE_SCORES && row < Q) qn = q_inv_norm[row];
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t as = it % ACC, aphase = (it / ACC) & 1u;
-        const int n0 = t * bn;
+        const int n0 = t * BLOCK_N;
         float* gn = gn_smem + as * BLOCK_N;
         if (FUSE_NORM) {
           mbar_wait(gnfull_bar(as), aphase, 800 + as);   // norm warps published this tile's norms
@@ -506,10 +487,10 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         mbar_wait(tfull_bar(as), aphase, 400 + as);
         tcgen05_fence_after();
-        const int n_valid = min(bn, N - n0);
+        const int n_valid = min(BLOCK_N, N - n0);
         const float floor = WRITE_SCORES ? kNegInf : read_floor(row_floor, row, Q);
         epilogue_tile<KMAX, WRITE_SCORES>(tmem_base + lane_base + as * BLOCK_N, gn, n0, n_valid, row,
-                                          Q, N, qn, scores_out, top, floor, bn);
+                                          Q, N, qn, scores_out, top, floor);
         if (!WRITE_SCORES) publish_floor<KMAX>(row_floor, row, Q, top, floor);
         tcgen05_fence_before();
         __syncwarp();
@@ -1022,7 +1003,6 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
 // chunking for the pair kernel: units = (query-tile pair, gallery chunk) over sms/2 clusters
 Plan make_plan_pair(int64_t Q, int64_t N) {
   Plan p;
-  p.bn = BLOCK_N;
   const int clusters = num_sms() / 2;
   p.m_tiles = static_cast<int>((Q + 2 * BLOCK_M - 1) / (2 * BLOCK_M));  // pairs of query tiles
   p.n_tiles = static_cast<int>((N + BLOCK_N - 1) / BLOCK_N);
@@ -1233,7 +1213,7 @@ irr_status launch(const QueryMaps& qm, const CUtensorMap& tg, const float* gin, 
                                                 static_cast<int>(N), num_kb, k, p.m_tiles,
                                                 p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
                                                 scores, g_policy, eps, qm.tail_tile, qm.tail_bytes,
-                                                row_floor, f16 ? 1 : 0, p.bn);
+                                                row_floor, f16 ? 1 : 0);
   if (!WS) profile_mark_stop(st);
   IRR_LAUNCH_CHECK();
   return IRR_OK;
@@ -1247,7 +1227,7 @@ size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
   // the caller may or may not pass cached norms: size for the larger of the two plans
   size_t parts = 0;
   for (int cached = 0; cached < 2; ++cached) {
-    const Plan p = use_pair(Q, cached) ? make_plan_pair(Q, N) : make_plan(Q, N, true);
+    const Plan p = use_pair(Q, cached) ? make_plan_pair(Q, N) : make_plan(Q, N);
     const size_t n = static_cast<size_t>(p.n_chunks) * Q * k;
     if (n > parts) parts = n;
   }
@@ -1266,7 +1246,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   if (ws_bytes < bf16_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
   const bool cached = g_inv_norm != nullptr;
   const bool pair = use_pair(Q, cached);
-  const Plan p = pair ? make_plan_pair(Q, N) : make_plan(Q, N, true);
+  const Plan p = pair ? make_plan_pair(Q, N) : make_plan(Q, N);
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* gin_ws = reinterpret_cast<float*>(w);
   w += align_up(static_cast<size_t>(N) * 4, 256);
@@ -1289,7 +1269,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   QueryMaps qm;
   CUtensorMap tg;
   if (!encode_queries(&qm, q, Q, D, f16) ||
-      !encode_bf16_rows(&tg, g, N, D, pair ? P_B_ROWS : p.bn, f16))
+      !encode_bf16_rows(&tg, g, N, D, pair ? P_B_ROWS : BLOCK_N, f16))
     return IRR_ERR_UNSUPPORTED_DEVICE;
   const CUtensorMap& tq = qm.full;
   irr_status s = IRR_OK;
