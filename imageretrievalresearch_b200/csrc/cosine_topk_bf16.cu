@@ -67,6 +67,7 @@ struct Knobs {
   int producers_min_pairs;   // IRR_NORMS_MIN_PAIRS: query-tile pairs from which the producers are used
   int norm_ahead;            // IRR_NORM_AHEAD: tiles the producers may run ahead (negative = unpaced)
   bool fused_pair;           // IRR_FUSED_PAIR=0: no fused norms in the pair kernel (pre-pass instead)
+  bool pdl;                  // IRR_PDL=0: no programmatic dependent launches along a search's kernels
 };
 const Knobs& knobs() {
   static const Knobs k = []() {
@@ -80,6 +81,7 @@ const Knobs& knobs() {
     r.producers_min_pairs = num("IRR_NORMS_MIN_PAIRS", 3);
     r.norm_ahead = num("IRR_NORM_AHEAD", 2);
     r.fused_pair = !flag("IRR_FUSED_PAIR", '0');
+    r.pdl = !flag("IRR_PDL", '0');
     return r;
   }();
   return k;
@@ -349,6 +351,10 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // Programmatic dependent launch: the set-up above (barriers, TMEM, descriptor prefetch) may have
+  // overlapped the tail of the previous kernel in the stream (the workspace zeroing); nothing
+  // below touches global memory before that kernel has completed.  A no-op without the attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int total_units = m_tiles * n_chunks;
 
@@ -509,6 +515,9 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   }
 
+  // the partial-list merge may be scheduled now (it waits for this grid to complete and flush
+  // before it reads anything)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -1000,6 +1009,12 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
 }
 
+__global__ void __launch_bounds__(256) zero_words_kernel(uint32_t* __restrict__ p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0u;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // chunking for the pair kernel: units = (query-tile pair, gallery chunk) over sms/2 clusters
 Plan make_plan_pair(int64_t Q, int64_t N) {
   Plan p;
@@ -1208,14 +1223,25 @@ irr_status launch(const QueryMaps& qm, const CUtensorMap& tg, const float* gin, 
   // a gallery streamed by a single query tile is read exactly once: do not let it displace the
   // query tiles in L2; with several query tiles the gallery tiles are the L2-shared operand
   const uint64_t g_policy = p.m_tiles == 1 ? kPolicyEvictFirst : kPolicyEvictNormal;
+  // programmatic dependent launch: this kernel's set-up overlaps the workspace-zeroing kernel
+  // before it, and the partial-list merge after it is scheduled while this one drains
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_ALLOC;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (!WS && knobs().pdl) ? 1 : 0;
   if (!WS) profile_mark_start(st);
-  kern<<<p.grid, NUM_THREADS, SMEM_ALLOC, st>>>(qm.full, qm.tail, tg, gin, qin, static_cast<int>(Q),
-                                                static_cast<int>(N), num_kb, k, p.m_tiles,
-                                                p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi,
-                                                scores, g_policy, eps, qm.tail_tile, qm.tail_bytes,
-                                                row_floor, f16 ? 1 : 0);
+  const cudaError_t e = cudaLaunchKernelEx(
+      &cfg, kern, qm.full, qm.tail, tg, gin, qin, static_cast<int>(Q), static_cast<int>(N), num_kb,
+      static_cast<int>(k), p.m_tiles, p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi, scores,
+      g_policy, eps, qm.tail_tile, qm.tail_bytes, row_floor, f16 ? 1 : 0);
   if (!WS) profile_mark_stop(st);
-  IRR_LAUNCH_CHECK();
+  if (e != cudaSuccess) return static_cast<irr_status>(static_cast<int>(e));
   return IRR_OK;
 }
 
@@ -1259,12 +1285,18 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   w += align_up(static_cast<size_t>(Q) * 4, 256);
   uint32_t* tile_done = reinterpret_cast<uint32_t*>(w);
   int mode = pair ? pair_norm_mode(cached, p.m_tiles) : NORMS_CACHED;
-  // one memset: the rows' shared floors and (if used) the per-tile norm counters
-  IRR_CUDA_TRY(cudaMemsetAsync(
-      row_floor, 0,
+  // zero the rows' shared floors and (if used) the per-tile norm counters: a memset, or — in front
+  // of the single-CTA kernel, whose set-up then overlaps it — a kernel
+  const size_t zero_bytes =
       mode == NORMS_PRODUCERS ? align_up(static_cast<size_t>(Q) * 4, 256) + static_cast<size_t>(p.n_tiles) * 4
-                              : static_cast<size_t>(Q) * 4,
-      st));
+                              : static_cast<size_t>(Q) * 4;
+  if (!pair && knobs().pdl) {
+    zero_words_kernel<<<static_cast<unsigned>((zero_bytes / 4 + 255) / 256), 256, 0, st>>>(
+        row_floor, static_cast<int>(zero_bytes / 4));
+    IRR_LAUNCH_CHECK();
+  } else {
+    IRR_CUDA_TRY(cudaMemsetAsync(row_floor, 0, zero_bytes, st));
+  }
 
   QueryMaps qm;
   CUtensorMap tg;

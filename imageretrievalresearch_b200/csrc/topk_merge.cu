@@ -25,6 +25,9 @@ merge_partials_kernel(const float* __restrict__ part_val, const int32_t* __restr
                       int64_t* __restrict__ out_idx) {
   const int lane = threadIdx.x & 31;
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * WARPS + (threadIdx.x >> 5);
+  // programmatic dependent launch: scheduled while the top-k kernel drains; its partial lists are
+  // complete and visible once this returns (a no-op when launched without the attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (qi >= Q) return;
 
   // query norm
@@ -144,13 +147,22 @@ irr_status merge_partials(const float* part_val, const int32_t* part_idx, int32_
                           int64_t idx_offset, float* out_val, int64_t* out_idx, cudaStream_t st) {
   if (Q == 0) return IRR_OK;
   const int grid = static_cast<int>((Q + WARPS - 1) / WARPS);
-  if (k <= 4)
-    merge_partials_kernel<4><<<grid, THREADS, 0, st>>>(part_val, part_idx, S, Q, k, q, D,
-                                                       static_cast<int>(dt), eps, idx_offset, out_val, out_idx);
-  else
-    merge_partials_kernel<16><<<grid, THREADS, 0, st>>>(part_val, part_idx, S, Q, k, q, D,
-                                                        static_cast<int>(dt), eps, idx_offset, out_val, out_idx);
-  IRR_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const int iS = S, ik = k, iD = D, idt = static_cast<int>(dt);
+  const cudaError_t e =
+      k <= 4 ? cudaLaunchKernelEx(&cfg, merge_partials_kernel<4>, part_val, part_idx, iS, Q, ik, q, iD,
+                                  idt, eps, idx_offset, out_val, out_idx)
+             : cudaLaunchKernelEx(&cfg, merge_partials_kernel<16>, part_val, part_idx, iS, Q, ik, q, iD,
+                                  idt, eps, idx_offset, out_val, out_idx);
+  if (e != cudaSuccess) return static_cast<irr_status>(static_cast<int>(e));
   return IRR_OK;
 }
 
