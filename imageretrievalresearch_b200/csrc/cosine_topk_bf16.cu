@@ -5,9 +5,9 @@
 // inference/training_analysis.ipynb:231-251) for all query rows in one launch.
 //
 // Layout / roles of the single-CTA kernel (one persistent CTA per SM, 384 threads; the CTA-pair
-// kernel further down is the cta_group::2 variant for large batches):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles of Q (128 or 256 x 64) and G (256 x 64),
-//               128-byte swizzle, into a 4- or 3-stage shared-memory ring (48 / 64 KB per stage)
+// kernel further down is the cta_group::2 variant for more than 128 queries):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles of Q (128 x 64) and G (256 x 64),
+//               128-byte swizzle, into a 4-stage shared-memory ring (48 KB per stage)
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256, K=16) x4 per stage,
 //               fp32 accumulators in TMEM, two accumulator stages (2 x 256 of the 512 columns)
 //   warp 2      TMEM allocator
