@@ -83,7 +83,7 @@ def test_every_octet_exactly_once_in_key_order(Q, N):
 
 
 @pytest.mark.parametrize("Q,N", [(600, 3000), (1024, 50_000), (40_000, 7_777), (4096, 40_000), (513, 257)])
-@pytest.mark.parametrize("ahead", [0, 2])
+@pytest.mark.parametrize("ahead", [0, 1, 2])
 def test_paced_producers_and_waiting_consumers_always_finish(Q, N, ahead):
     m_pairs, n_tiles, tpc, n_chunks, C = plan_pair(Q, N)
     total_units = m_pairs * n_chunks
