@@ -909,14 +909,17 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int chunk = c_lo + r2 / OCTETS_PER_TILE;
       const int oct = r2 % OCTETS_PER_TILE;
       const int tile = chunk * tiles_per_chunk + j;
-      if (tile >= n_tiles) continue;
       if (paced) {
+        // The CTA's four producer warps take four consecutive slots per round — same tile position,
+        // same key — so ONE of them polls the position and the others wait for it at a named
+        // barrier, which costs no issue slots (polled by all four, this loop alone was a third of
+        // the kernel's executed instructions: nanosleep returns after ~80 ns whatever it is asked).
         const int key = w * tiles_per_chunk + j;
-        // a tile takes ~10 us of MMAs whatever the batch size: polling the position every ~1.5 us
-        // keeps the lead (at 256 ns this loop alone was a third of the kernel's executed
-        // instructions: 123 k polls per warp and launch)
-        while (key > *stream_pos + norm_ahead) __nanosleep(1500);
+        if (norm_warp_index(warp) == 0)
+          while (key > *stream_pos + norm_ahead) __nanosleep(1500);
+        named_bar_sync(2, NORM_THREADS);
       }
+      if (tile >= n_tiles) continue;
       const int row0 = tile * BLOCK_N + oct * OCTET;
       if (row0 >= N) continue;
       const int rows = min(OCTET, N - row0);
@@ -950,8 +953,12 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         const int n0 = t * BLOCK_N;
         float* gn = gn_smem + as * BLOCK_N;
+        // One epilogue warp waits on the mbarriers (norms published, accumulator ready); the other
+        // three wait for it at the named barrier below, where a waiting warp issues nothing — the
+        // epilogue idles ~80 % of a tile's time, and four warps polling was a sixth of the kernel's
+        // executed instructions.
         if (NORMS == NORMS_FUSED) {
-          mbar_wait_cluster(gnfull_bar(as), aphase, 1600 + as);   // both halves' norms have landed
+          if (ew == 0) mbar_wait_cluster(gnfull_bar(as), aphase, 1600 + as);   // both halves' norms have landed
         } else {
           const int c0 = n0 + et, c1 = n0 + et + EPI_THREADS;
           if (NORMS_INSIDE) {
@@ -968,9 +975,9 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
             gn[et] = c0 < N ? __ldg(g_inv_norm + c0) : 0.0f;
             gn[et + EPI_THREADS] = c1 < N ? __ldg(g_inv_norm + c1) : 0.0f;
           }
-          named_bar_sync(1, EPI_THREADS);
         }
-        mbar_wait(tfull_bar(as), aphase, 1400 + as);
+        if (ew == 0) mbar_wait(tfull_bar(as), aphase, 1400 + as);
+        named_bar_sync(1, EPI_THREADS);
         tcgen05_fence_after();
         const int n_valid = min(BLOCK_N, N - n0);
         const float floor = read_floor(row_floor, row, Q);
