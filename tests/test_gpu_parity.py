@@ -506,11 +506,16 @@ def test_dispatch_regime_sweep(Q, D, N):
     norms, k in {3, 10, 16} (KMAX = 4 / 16), ragged N (last tile and last chunk partial), on a
     gallery with exact duplicate rows (ties -> lower index) — against the fp64 oracle of
     train/train_efficient_cos_con_ce_loss.py:273-276 on the same bf16-valued inputs:
-      Q <= 128              launch<KM,false,FN,1>     FN = fused norm warps when uncached
-      129..256 cached       launch_pair<KM, cached>   one CTA pair streams the gallery once
-      129..256 uncached     launch_pair<KM, fused>    norms from the staged tiles (both CTAs)
-      257..384              launch<KM,false,false,1> cached / launch_pair<KM, fused> uncached
-      >= 385                launch_pair<KM, cached|fused>
+      Q <= 128 (128)                  launch<KM, false, FN>   FN = fused norm warps when uncached
+      129..256 (129, 256) cached      launch_pair<KM, NORMS_CACHED>   one CTA pair streams the gallery once
+      129..256 uncached               launch_pair<KM, NORMS_FUSED>    norms from the staged tiles, DSMEM
+      257..384 (257, 384) cached      launch<KM, false, false>        three single-CTA query tiles
+      257..384 uncached               launch_pair<KM, NORMS_FUSED>    ragged / absent second pair tile
+      385..512 (385, 512)             launch_pair<KM, NORMS_CACHED | NORMS_FUSED>
+      > 512 (513, 768, 1100) cached   launch_pair<KM, NORMS_CACHED>
+      > 512 uncached                  launch_pair<KM, NORMS_PRODUCERS>  cooperative launch, paced producers
+    with KM = 4 for k = 3 and KM = 16 for k = 10, 16 (launch<4, true, false>, the score-writing
+    instantiation, is test_bf16_dense_scores / the large-k tests).
     """
     q, gal = synthetic.tied_gallery(N, D, Q, seed=Q + D, dtype=torch.bfloat16)
     s = ref.cos_scores(q, gal)
