@@ -65,18 +65,6 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n"
-      ".reg .pred P;\n"
-      "elect.sync _|P, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, P;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // two packed bf16 (one 32-bit word) -> two fp32, exact
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -398,11 +386,6 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, bool f16) {
   return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) |
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
-}
-// instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, shape M x N
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
