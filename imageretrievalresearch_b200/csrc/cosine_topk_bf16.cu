@@ -1023,7 +1023,16 @@ __global__ void __launch_bounds__(256) zero_words_kernel(uint32_t* __restrict__ 
 }
 
 // chunking for the pair kernel: units = (query-tile pair, gallery chunk) over sms/2 clusters
-Plan make_plan_pair(int64_t Q, int64_t N) {
+// The m_pairs clusters that walk a chunk together fetch each of its gallery tiles from DRAM once
+// (the other m_pairs - 1 reads hit L2).  clusters / m_pairs is not whole, so one chunk per wave
+// straddles into the next wave, where its late units stream it AGAIN — one wave after the first
+// pass, and a wave of long chunks moves more bytes than L2 holds: at 4096 queries (16 pairs on 74
+// clusters, 4.6 chunks per wave of 53 tiles = 193 MB) every fifth chunk was read twice, 3.77 GB of
+// DRAM reads for 3.08 GB of gallery.  From 12 pairs on (a straddler is >= 15 % of a wave) the
+// chunks are therefore kept short enough that a wave's tiles stay in L2 until the late units
+// come by: 8 tiles at 4096 x 1536 -> 3.12 GB, same kernel time (profiles/r02_notes.md).
+constexpr size_t WAVE_L2_BUDGET = 32u << 20;   // a quarter of the 126 MB L2
+Plan make_plan_pair(int64_t Q, int64_t N, int32_t D) {
   Plan p;
   const int clusters = num_sms() / 2;
   p.m_tiles = static_cast<int>((Q + 2 * BLOCK_M - 1) / (2 * BLOCK_M));  // pairs of query tiles
@@ -1031,7 +1040,13 @@ Plan make_plan_pair(int64_t Q, int64_t N) {
   if (p.n_tiles < 1) p.n_tiles = 1;
   int best_tpc = 1;
   double best_cost = 1e300;
-  const int max_tpc = p.n_tiles < 64 ? p.n_tiles : 64;
+  int max_tpc = p.n_tiles < 64 ? p.n_tiles : 64;
+  if (p.m_tiles >= 12) {
+    const size_t chunks_per_wave = static_cast<size_t>((clusters + p.m_tiles - 1) / p.m_tiles);
+    const size_t tile_bytes = static_cast<size_t>(BLOCK_N) * static_cast<size_t>(D > 0 ? D : 1) * 2;
+    const int cap = static_cast<int>(WAVE_L2_BUDGET / (chunks_per_wave * tile_bytes));
+    max_tpc = std::min(max_tpc, std::max(cap, 4));
+  }
   for (int tpc = 1; tpc <= max_tpc; ++tpc) {
     const int chunks = (p.n_tiles + tpc - 1) / tpc;
     const long long units = 1ll * chunks * p.m_tiles;
@@ -1256,11 +1271,11 @@ irr_status launch(const QueryMaps& qm, const CUtensorMap& tg, const float* gin, 
 
 // workspace: [g_inv_norm fp32 N][part_val fp32 chunks*Q*k][part_idx i32 chunks*Q*k]
 //            [row_floor u32 Q | tile_rows_done u32 n_tiles]   (the last two are zeroed per call)
-size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k) {
+size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t k) {
   // the caller may or may not pass cached norms: size for the larger of the two plans
   size_t parts = 0;
   for (int cached = 0; cached < 2; ++cached) {
-    const Plan p = use_pair(Q, cached) ? make_plan_pair(Q, N) : make_plan(Q, N);
+    const Plan p = use_pair(Q, cached) ? make_plan_pair(Q, N, D) : make_plan(Q, N);
     const size_t n = static_cast<size_t>(p.n_chunks) * Q * k;
     if (n > parts) parts = n;
   }
@@ -1276,10 +1291,10 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   if (device_cc() / 10 != 10) return IRR_ERR_UNSUPPORTED_DEVICE;
   const bool f16 = dt == IRR_F16;
   if (N > 0x7fffff00ll || Q > 0x7fffff00ll) return IRR_ERR_INVALID_ARG;
-  if (ws_bytes < bf16_topk_workspace_bytes(Q, N, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
+  if (ws_bytes < bf16_topk_workspace_bytes(Q, N, D, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
   const bool cached = g_inv_norm != nullptr;
   const bool pair = use_pair(Q, cached);
-  const Plan p = pair ? make_plan_pair(Q, N) : make_plan(Q, N);
+  const Plan p = pair ? make_plan_pair(Q, N, D) : make_plan(Q, N);
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* gin_ws = reinterpret_cast<float*>(w);
   w += align_up(static_cast<size_t>(N) * 4, 256);

@@ -167,7 +167,7 @@ size_t irr_cosine_topk_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t 
   (void)D;
   if (Q < 0 || N < 0 || k < 1) return 0;
   if (k > IRR_MAX_K_FUSED) return large_k_workspace_bytes(Q, N);
-  return dt != IRR_F32 ? bf16_topk_workspace_bytes(Q, N, k) : f32_topk_workspace_bytes(Q, N, k);
+  return dt != IRR_F32 ? bf16_topk_workspace_bytes(Q, N, D, k) : f32_topk_workspace_bytes(Q, N, k);
 }
 
 irr_status irr_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,

@@ -43,7 +43,7 @@ irr_status topk_exchange_merge(const float* local_val, const int64_t* local_idx,
                                cudaStream_t st);
 
 // cosine_topk_bf16.cu (tcgen05 / TMA)
-size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t k);
+size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t k);
 irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_norm, int64_t Q,
                             int64_t N, int32_t D, int32_t k, float eps, int64_t idx_offset,
                             float* out_val, int64_t* out_idx, void* ws, size_t ws_bytes,

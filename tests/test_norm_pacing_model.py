@@ -16,13 +16,17 @@ BLOCK_M, BLOCK_N, OCTETS = 128, 256, 32
 SMS = 148
 
 
-def plan_pair(Q, N):
-    """make_plan_pair()"""
+def plan_pair(Q, N, D=1536):
+    """make_plan_pair(): chunks short enough that a wave's tiles stay in L2 from 12 pairs on"""
     clusters = SMS // 2
     m_pairs = (Q + 2 * BLOCK_M - 1) // (2 * BLOCK_M)
     n_tiles = max((N + BLOCK_N - 1) // BLOCK_N, 1)
     best, best_cost = 1, 1e300
-    for tpc in range(1, min(n_tiles, 64) + 1):
+    max_tpc = min(n_tiles, 64)
+    if m_pairs >= 12:
+        chunks_per_wave = (clusters + m_pairs - 1) // m_pairs
+        max_tpc = min(max_tpc, max((32 << 20) // (chunks_per_wave * BLOCK_N * D * 2), 4))
+    for tpc in range(1, max_tpc + 1):
         chunks = (n_tiles + tpc - 1) // tpc
         waves = (chunks * m_pairs + clusters - 1) // clusters
         cost = waves * (tpc + 0.35)
