@@ -537,6 +537,32 @@ def test_dispatch_regime_sweep(Q, D, N):
         assert (unc.values[:, 0] == unc.values[:, 1]).all()
 
 
+def test_many_pairs_short_chunks():
+    """Thirteen query-tile pairs (Q = 3100, ragged last pair) over 235 gallery tiles: from twelve
+    pairs on make_plan_pair keeps chunks short (here 7 tiles -> 34 chunks, 442 units in six waves
+    on 74 clusters, every wave ending in a chunk that straddles into the next), cached norms and
+    the paced in-kernel producers; 34 partial lists per query through the merge.  Against the fp64
+    oracle of train/train_efficient_cos_con_ce_loss.py:273-276 on a gallery with duplicate rows."""
+    Q, N, D = 3100, 60_013, 1536
+    q, gal = synthetic.tied_gallery(N, D, Q, seed=31, dtype=torch.bfloat16)
+    qd, gd = q.cuda(), gal.cuda()
+    handle = irr.Gallery(gd)
+    # oracle on the GPU in fp64 by blocks (3100 x 60013 x 1536 is minutes on the host cores)
+    qn = torch.nn.functional.normalize(qd.double(), dim=1)
+    gn = torch.nn.functional.normalize(gd.double(), dim=1)
+    s = (qn @ gn.T).cpu()
+    ov, oi = torch.sort(s, dim=1, descending=True, stable=True)
+    ov, oi = ov[:, :10], oi[:, :10]
+    for k in (3, 10):
+        unc = irr.cosine_topk(qd, gd, k)
+        cac = handle.search(qd, k)
+        _check_sorted(unc, s, ov, oi, k, 1e-4)
+        _check_sorted(cac, s, ov, oi, k, 1e-4)
+        assert torch.equal(cac.indices, unc.indices)
+        assert (unc.indices[:, 0] < unc.indices[:, 1]).all()
+        assert (unc.values[:, 0] == unc.values[:, 1]).all()
+
+
 def test_config5_scaled_down_k10_q8192_d2560():
     """BASELINE.json configs[4] (10M x 2560 bf16, Q=8192, k=10 over 8 GPUs) scaled to one eighth of
     one GPU's shard: N = 160,000 rows, the same Q, k, D — the kernel instantiation the full config
