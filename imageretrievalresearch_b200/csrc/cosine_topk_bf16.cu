@@ -229,27 +229,29 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, i
   }
 }
 
-// Fused-norm warps: square-sum this thread's two gallery rows (64 elements each) of one stage.
-// Logical chunk order (position j ^ (row & 7) under the 128-byte swizzle), see the kernel.
+// Fused-norm warps: the running square-sum of one gallery row, four partial sums — (even, odd)
+// elements of the even and of the odd 16-byte chunks — so that one packed FFMA2 squares and adds
+// the two elements of a 32-bit word (the unpack + FMA instructions of these warps are what the
+// fused norms cost next to cached ones; packed, they are a quarter fewer).
+struct RowSq {
+  float2 a, b;
+  __device__ __forceinline__ void reset() { a = make_float2(0.f, 0.f); b = a; }
+  __device__ __forceinline__ float total() const { return (a.x + a.y) + (b.x + b.y); }
+};
+// One 128-byte slice (64 elements) of ONE gallery row out of a staged tile, in logical chunk order
+// (position j ^ (row & 7) under the 128-byte swizzle: conflict-free and independent of where the
+// row sits, so duplicate rows get bit-identical norms — in every fused-norm variant).
 template <bool F16>
-__device__ __forceinline__ void norm_stage_sums(const uint4* r0, const uint4* r1, int nt, float& s0a,
-                                                float& s0b, float& s1a, float& s1b) {
+__device__ __forceinline__ void norm_row_sums(const uint4* r, int nt, RowSq& s) {
 #pragma unroll
   for (int j = 0; j < 8; j += 2) {
-    const uint4 u0 = r0[j ^ (nt & 7)], u1 = r0[(j + 1) ^ (nt & 7)];
-    const uint4 w0 = r1[j ^ (nt & 7)], w1 = r1[(j + 1) ^ (nt & 7)];
+    const uint4 u0 = r[j ^ (nt & 7)], u1 = r[(j + 1) ^ (nt & 7)];
     const uint32_t x0[4] = {u0.x, u0.y, u0.z, u0.w}, x1[4] = {u1.x, u1.y, u1.z, u1.w};
-    const uint32_t y0[4] = {w0.x, w0.y, w0.z, w0.w}, y1[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float2 f = unpack16x2(x0[e], F16);
-      s0a = fmaf(f.x, f.x, s0a); s0a = fmaf(f.y, f.y, s0a);
-      f = unpack16x2(x1[e], F16);
-      s0b = fmaf(f.x, f.x, s0b); s0b = fmaf(f.y, f.y, s0b);
-      f = unpack16x2(y0[e], F16);
-      s1a = fmaf(f.x, f.x, s1a); s1a = fmaf(f.y, f.y, s1a);
-      f = unpack16x2(y1[e], F16);
-      s1b = fmaf(f.x, f.x, s1b); s1b = fmaf(f.y, f.y, s1b);
+      const float2 f0 = unpack16x2(x0[e], F16), f1 = unpack16x2(x1[e], F16);
+      s.a = __ffma2_rn(f0, f0, s.a);
+      s.b = __ffma2_rn(f1, f1, s.b);
     }
   }
 }
@@ -436,7 +438,9 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t0 = chunk * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
       for (int t = t0; t < t1; ++t, ++it) {
-        float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
+        RowSq s0, s1;
+        s0.reset();
+        s1.reset();
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, 600 + stage);
           const uint8_t* b = smem_gen + stage * STAGE_BYTES + G::A_BYTES;
@@ -444,8 +448,8 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint4* r1 = reinterpret_cast<const uint4*>(b + (nt + NORM_THREADS) * 128);
           // one branch per stage, not one select per element: these four warps have to keep pace
           // with the HBM stream
-          if (is_f16) norm_stage_sums<true>(r0, r1, nt, s0a, s0b, s1a, s1b);
-          else        norm_stage_sums<false>(r0, r1, nt, s0a, s0b, s1a, s1b);
+          if (is_f16) { norm_row_sums<true>(r0, nt, s0); norm_row_sums<true>(r1, nt, s1); }
+          else        { norm_row_sums<false>(r0, nt, s0); norm_row_sums<false>(r1, nt, s1); }
           __syncwarp();
           if (lane == 0) mbar_arrive(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -454,8 +458,8 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // the epilogue must be done with the norms it last read from this buffer
         mbar_wait(tempty_bar(as), aphase ^ 1u, 700 + as);
         float* gn = gn_smem + as * BLOCK_N;
-        gn[nt] = 1.0f / fmaxf(sqrtf(s0a + s0b), eps);
-        gn[nt + NORM_THREADS] = 1.0f / fmaxf(sqrtf(s1a + s1b), eps);
+        gn[nt] = 1.0f / fmaxf(sqrtf(s0.total()), eps);
+        gn[nt + NORM_THREADS] = 1.0f / fmaxf(sqrtf(s1.total()), eps);
         __syncwarp();
         if (lane == 0) mbar_arrive(gnfull_bar(as));
       }
@@ -654,25 +658,6 @@ __device__ __forceinline__ void norm_octet(const uint4* __restrict__ g_rows, int
   }
 }
 
-// One square-summed 128-byte slice (64 elements) of ONE gallery row out of a staged tile, same
-// logical chunk order and accumulator split as norm_stage_sums (so every fused-norm variant gives a
-// row the same bits wherever it sits).
-template <bool F16>
-__device__ __forceinline__ void norm_row_sums(const uint4* r, int nt, float& sa, float& sb) {
-#pragma unroll
-  for (int j = 0; j < 8; j += 2) {
-    const uint4 u0 = r[j ^ (nt & 7)], u1 = r[(j + 1) ^ (nt & 7)];
-    const uint32_t x0[4] = {u0.x, u0.y, u0.z, u0.w}, x1[4] = {u1.x, u1.y, u1.z, u1.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f = unpack16x2(x0[e], F16);
-      sa = fmaf(f.x, f.x, sa); sa = fmaf(f.y, f.y, sa);
-      f = unpack16x2(x1[e], F16);
-      sb = fmaf(f.x, f.x, sb); sb = fmaf(f.y, f.y, sb);
-    }
-  }
-}
-
 // Where the inverse gallery norms of the pair kernel come from (template parameter NORMS):
 //
 // NORMS_FUSED (no cached norms, one or two query-tile pairs): L2-normalisation fused into the load.
@@ -855,12 +840,13 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t0 = chunk * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
       for (int t = t0; t < t1; ++t, ++it) {
-        float sa = 0.f, sb = 0.f;
+        RowSq sq;
+        sq.reset();
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase, 1500 + stage);   // the stage's MMAs have retired
           const uint4* r = reinterpret_cast<const uint4*>(smem_gen + stage * P_STAGE_BYTES + P_A_BYTES + nt * 128);
-          if (f16) norm_row_sums<true>(r, nt, sa, sb);
-          else     norm_row_sums<false>(r, nt, sa, sb);
+          if (f16) norm_row_sums<true>(r, nt, sq);
+          else     norm_row_sums<false>(r, nt, sq);
           __syncwarp();
           if (lane == 0) mbar_arrive(normdone_bar(stage));   // the producer may refill the stage
           if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
@@ -870,7 +856,7 @@ cosine_topk_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // "accumulator drained" barrier (the norm warps may be several short tiles ahead of the MMAs)
         const uint32_t as = it & 1u;
         mbar_wait_cluster(tempty_bar(as), ((it >> 1) & 1u) ^ 1u, 1700 + as);
-        const float inv = 1.0f / fmaxf(sqrtf(sa + sb), eps);
+        const float inv = 1.0f / fmaxf(sqrtf(sq.total()), eps);
         float* mine = gn_smem + as * BLOCK_N + static_cast<int>(rank) * P_B_ROWS + nt;
         *mine = inv;
         st_shared_cluster_f32(mapa_rank(smem_u32(mine), peer), inv);
