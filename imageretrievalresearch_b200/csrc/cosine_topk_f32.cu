@@ -3,11 +3,14 @@
 // and tie rule as the bf16 tensor-core kernel.  Replaces cos(q[i][None], G) + torch.topk(sim, k)
 // (train/train_efficient_cos_con_ce_loss.py:273-276,385-388; ipynb:238) for fp32 embeddings.
 //
-// CTA = 256 threads, score tile 64 queries x 128 gallery rows, K-slabs of 16 staged transposed in
-// shared memory with register prefetch; each thread owns a 4 x 8 register micro-tile.  The scaled
-// tile goes to shared memory once, and 64 threads (one per query row) fold it into their running
-// sorted top-k in increasing column order.  Work unit = (query tile, chunk of gallery tiles); the
-// per-unit partial lists are folded by topk_merge.cu.
+// CTA = 128 threads, score tile 64 queries x 64 gallery rows (three CTAs per SM: a 10k-row gallery
+// split over K is 314 CTAs, all resident at once), K-slabs of 16 staged row-major in a
+// four-deep cp.async ring (a slab is in flight for three slabs' worth of FMAs: with one slab of
+// register prefetch the kernel waited on every load — long-scoreboard stalls were its largest
+// stall reason and a slab took 3060 cycles against 1120 of instruction issue); each thread owns a
+// 4 x 8 register micro-tile.  The scaled tile goes to shared memory once, and 64 threads (one per
+// query row) fold it into their running sorted top-k in increasing column order.  Work unit =
+// (query tile, chunk of gallery tiles); the per-unit partial lists are folded by topk_merge.cu.
 #include <stdlib.h>
 
 #include "irr_common.cuh"
@@ -16,13 +19,28 @@
 namespace irr {
 namespace {
 
-constexpr int BM = 64, BN = 128, BK = 16;
-constexpr int THREADS = 256;
-constexpr int A_LD = BM + 4, B_LD = BN + 4, S_LD = BN + 1;
-constexpr int SMEM_A = 2 * BK * A_LD * 4;
-constexpr int SMEM_B = 2 * BK * B_LD * 4;
+constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int THREADS = 256;     // large-batch kernel
+constexpr int S_THREADS = 128;   // small kernel: 16 x 8 threads, 4 x 8 outputs each
+constexpr int S_LD = BN + 1;
+// small kernel: ring of ST slabs, rows of BK floats padded to 80 bytes — an odd number of 16-byte
+// units, so the LDS.128 of eight consecutive rows hit eight different bank groups
+constexpr int ST = 4;
+constexpr int ROW_LD = BK + 4;
+constexpr int SMEM_A = ST * BM * ROW_LD * 4;
+constexpr int SMEM_B = ST * BN * ROW_LD * 4;
 constexpr int SMEM_S = BM * S_LD * 4;
-constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_S;
+constexpr int SMEM_L = BM * 16 * 8;   // running top-k lists between tiles (KMAX <= 16), kept out of
+                                     // the registers the FMA loop needs
+constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_S + SMEM_L;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  // src_bytes = 0: the 16 destination bytes are zero-filled (rows / k past the end)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct Plan {
   int m_tiles, n_tiles, tiles_per_chunk, n_chunks;
@@ -34,7 +52,7 @@ Plan make_plan(int64_t Q, int64_t N) {
   p.n_tiles = static_cast<int>((N + BN - 1) / BN);
   if (p.m_tiles < 1) p.m_tiles = 1;
   if (p.n_tiles < 1) p.n_tiles = 1;
-  const int slots = num_sms() * 2;  // two resident CTAs per SM
+  const int slots = num_sms() * 3;  // three resident CTAs per SM
   int best = 1;
   double best_cost = 1e300;
   const int max_tpc = p.n_tiles < 64 ? p.n_tiles : 64;
@@ -52,7 +70,8 @@ Plan make_plan(int64_t Q, int64_t N) {
 // WRITE_SCORES: instead of selecting, publish the dense cosine tile (both norms applied) — the
 // first stage of the large-k path (topk_select.cu).
 //
-// Every dot product is summed as (first half of K) + (second half of K), each half in ascending k.
+// Every dot product is summed as (first half of K) + (second half of K), each half as (its even
+// k, ascending) + (its odd k, ascending) — the two lanes of the packed FFMA2 accumulators.
 // SPLIT = 1: one CTA runs both halves (the first half's partial tile waits in its score buffer).
 // SPLIT = 2: a cluster of two CTAs runs one half each and the second CTA hands its partial tile to
 // the first through distributed shared memory — for searches with too few gallery tiles to give
@@ -60,32 +79,46 @@ Plan make_plan(int64_t Q, int64_t N) {
 // so the two variants return identical bits and a gallery scanned in blocks (StreamedGallery)
 // ranks exactly like the resident one whichever variant each block size selects.
 template <int KMAX, bool WRITE_SCORES, int SPLIT>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(S_THREADS, 3)
 cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
                        const float* __restrict__ g_inv_norm, int Q, int N, int D, int k,
                        int m_tiles, int n_tiles, int tiles_per_chunk,
                        float* __restrict__ part_val, int32_t* __restrict__ part_idx,
                        const float* __restrict__ q_inv_norm, float* __restrict__ scores_out) {
   extern __shared__ __align__(16) uint8_t smem[];
-  float* As = reinterpret_cast<float*>(smem);                      // [2][BK][A_LD]
-  float* Bs = reinterpret_cast<float*>(smem + SMEM_A);             // [2][BK][B_LD]
+  float* As = reinterpret_cast<float*>(smem);                      // [ST][BM][ROW_LD]
+  float* Bs = reinterpret_cast<float*>(smem + SMEM_A);             // [ST][BN][ROW_LD]
   float* Ss = reinterpret_cast<float*>(smem + SMEM_A + SMEM_B);    // [BM][S_LD]
+  float* Lv = reinterpret_cast<float*>(smem + SMEM_A + SMEM_B + SMEM_S);   // [KMAX][BM]
+  int32_t* Li = reinterpret_cast<int32_t*>(Lv + BM * KMAX);
+  const uint32_t as_u32 = smem_u32(As), bs_u32 = smem_u32(Bs);
 
   const int t = threadIdx.x;
-  const int ty = t >> 4, tx = t & 15;
+  const int ty = t >> 3, tx = t & 7;
   const int unit = blockIdx.x / SPLIT;
   const uint32_t rank = SPLIT == 2 ? cluster_ctarank() : 0u;   // which half of K this CTA sums
   const int chunk = unit / m_tiles, mt = unit - chunk * m_tiles;
   const int m0 = mt * BM;
   const int t0 = chunk * tiles_per_chunk, t1 = min(t0 + tiles_per_chunk, n_tiles);
 
-  // global -> smem staging assignment: A: one float4 / thread, B: two float4 / thread
-  const int a_row = t >> 2, a_kq = (t & 3) * 4;
-  const bool a_ok = m0 + a_row < Q;
-  const float* a_src = q + static_cast<size_t>(a_ok ? m0 + a_row : 0) * D + a_kq;
+  // global -> smem staging assignment: a slab row is four 16-byte pieces, two of A and two of B
+  // per thread.  This thread's micro-tile: query rows ty*4 + i, gallery rows tx + 8*j.
+  const float* a_src[2];
+  bool a_ok[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int f = t + i * S_THREADS;
+    a_ok[i] = m0 + (f >> 2) < Q;
+    a_src[i] = q + static_cast<size_t>(a_ok[i] ? m0 + (f >> 2) : 0) * D + (f & 3) * 4;
+  }
 
-  TopKList<KMAX, int32_t> top;
-  top.reset();
+  if (!WRITE_SCORES && t < BM) {   // (read again only by this thread: no barrier needed)
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      Lv[j * BM + t] = kNegInf;
+      Li[j * BM + t] = -1;
+    }
+  }
 
   const int num_ks = (D + BK - 1) / BK;
   const int half_ks = (num_ks + 1) / 2;
@@ -98,94 +131,112 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
     bool b_ok[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int f = t + i * THREADS;
+      const int f = t + i * S_THREADS;
       const int row = f >> 2;
       b_ok[i] = n0 + row < N;
       b_src[i] = g + static_cast<size_t>(b_ok[i] ? n0 + row : 0) * D + (f & 3) * 4;
     }
+    // packed accumulators: .x sums the even k of a K-half, .y the odd k (one FFMA2 per two k)
+    float2 acc2[4][8];
     float acc[4][8];
+    auto zero_acc = [&]() {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j) acc2[i][j] = make_float2(0.f, 0.f);
+    };
+    auto fold_acc = [&]() {   // a K-half's dot products: (even k) + (odd k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = acc2[i][j].x + acc2[i][j].y;
+    };
+    zero_acc();
 
-    float4 ra, rb[2];
-    auto gload = [&](int ks) {
+    // stage K-slab ks (16 k of the 64 query rows and of the tile's 128 gallery rows) into ring slot
+    auto issue = [&](int ks, int slot) {
       const int kk = ks * BK;
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      ra = (a_ok && kk + a_kq < D) ? __ldg(reinterpret_cast<const float4*>(a_src + kk)) : z;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int kq = ((t + i * THREADS) & 3) * 4;
-        rb[i] = (b_ok[i] && kk + kq < D) ? __ldg(reinterpret_cast<const float4*>(b_src[i] + kk)) : z;
-      }
-    };
-    auto sstore = [&](int buf) {
-      float* a = As + buf * BK * A_LD;
-      a[(a_kq + 0) * A_LD + a_row] = ra.x;
-      a[(a_kq + 1) * A_LD + a_row] = ra.y;
-      a[(a_kq + 2) * A_LD + a_row] = ra.z;
-      a[(a_kq + 3) * A_LD + a_row] = ra.w;
-      float* b = Bs + buf * BK * B_LD;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int f = t + i * THREADS;
+        const int f = t + i * S_THREADS;
         const int row = f >> 2, kq = (f & 3) * 4;
-        b[(kq + 0) * B_LD + row] = rb[i].x;
-        b[(kq + 1) * B_LD + row] = rb[i].y;
-        b[(kq + 2) * B_LD + row] = rb[i].z;
-        b[(kq + 3) * B_LD + row] = rb[i].w;
+        cp_async16(as_u32 + static_cast<uint32_t>((slot * BM + row) * ROW_LD + kq) * 4u, a_src[i] + kk,
+                   (a_ok[i] && kk + kq < D) ? 16u : 0u);
+        cp_async16(bs_u32 + static_cast<uint32_t>((slot * BN + row) * ROW_LD + kq) * 4u, b_src[i] + kk,
+                   (b_ok[i] && kk + kq < D) ? 16u : 0u);
       }
     };
-
-    // K-slabs [ks0, ks1) into acc (ascending k; slab ks sits in buffer (ks - ks0) & 1)
+    // K-slabs [ks0, ks1) into acc (ascending k; slab ks sits in ring slot (ks - ks0) % ST)
     auto run_k = [&](int ks0, int ks1) {
       if (ks0 >= ks1) return;
-      gload(ks0);
-      __syncthreads();  // previous readers of As/Bs (and of the previous tile's Ss) are done
-      sstore(0);
-      __syncthreads();
+      __syncthreads();  // previous readers of the ring (and of the previous tile's Ss) are done
+#pragma unroll
+      for (int s = 0; s < ST - 1; ++s) {
+        if (ks0 + s < ks1) issue(ks0 + s, s);
+        cp_async_commit();
+      }
       for (int ks = ks0; ks < ks1; ++ks) {
-        const int buf = (ks - ks0) & 1;
-        if (ks + 1 < ks1) gload(ks + 1);
-        const float* a = As + buf * BK * A_LD + ty * 4;
-        const float* b = Bs + buf * BK * B_LD + tx * 4;
+        cp_async_wait<ST - 2>();   // this thread's pieces of slab ks have landed ...
+        __syncthreads();           // ... everybody's have, and everybody is done with slab ks - 1,
+        const int nxt = ks + ST - 1;   // whose slot is refilled now
+        if (nxt < ks1) issue(nxt, (nxt - ks0) % ST);
+        cp_async_commit();         // (an empty group keeps the count uniform)
+        const int slot = (ks - ks0) % ST;
+        const float* a = As + (slot * BM + ty * 4) * ROW_LD;
+        const float* b = Bs + (slot * BN + tx) * ROW_LD;
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-          const float4 av = *reinterpret_cast<const float4*>(a + kk * A_LD);
-          const float4 b0 = *reinterpret_cast<const float4*>(b + kk * B_LD);
-          const float4 b1 = *reinterpret_cast<const float4*>(b + kk * B_LD + 64);
-          const float ar[4] = {av.x, av.y, av.z, av.w};
-          const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        for (int kq = 0; kq < BK; kq += 4) {
+          float4 av[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(a + i * ROW_LD + kq);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
-        }
-        if (ks + 1 < ks1) {
-          sstore(buf ^ 1);  // the other buffer was last read one iteration ago, before the sync below
-          __syncthreads();
+          for (int jh = 0; jh < 8; jh += 4) {   // four gallery rows at a time
+            float4 bv[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              bv[jj] = *reinterpret_cast<const float4*>(b + (jh + jj) * 8 * ROW_LD + kq);
+            // k0,k1 of all 16 outputs, then k2,k3: 16 independent FFMA2 between two that touch the
+            // same accumulator
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 a01 = make_float2(av[i].x, av[i].y);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                acc2[i][jh + jj] = __ffma2_rn(a01, make_float2(bv[jj].x, bv[jj].y), acc2[i][jh + jj]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 a23 = make_float2(av[i].z, av[i].w);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                acc2[i][jh + jj] = __ffma2_rn(a23, make_float2(bv[jj].z, bv[jj].w), acc2[i][jh + jj]);
+            }
+          }
         }
       }
     };
     // this thread's 4 x 8 elements of the score buffer (private to the thread: no barrier needed
     // between its own store and load)
     auto s_at = [&](int i, int j) -> float* {
-      return Ss + (ty * 4 + i) * S_LD + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      return Ss + (ty * 4 + i) * S_LD + tx + 8 * j;
     };
     if (SPLIT == 1) {
       run_k(0, half_ks);
+      fold_acc();
+      zero_acc();
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { *s_at(i, j) = acc[i][j]; acc[i][j] = 0.f; }
+        for (int j = 0; j < 8; ++j) *s_at(i, j) = acc[i][j];
       run_k(half_ks, num_ks);
+      fold_acc();
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = *s_at(i, j) + acc[i][j];      // first half + second half
     } else {
       if (rank == 0) run_k(0, half_ks); else run_k(half_ks, num_ks);
+      fold_acc();
       if (rank == 1) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -203,28 +254,36 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
     float gn[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      const int c = n0 + tx + 8 * j;
       gn[j] = c < N ? __ldg(g_inv_norm + c) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4);
-        Ss[(ty * 4 + i) * S_LD + c] = acc[i][j] * gn[j];
-      }
+      for (int j = 0; j < 8; ++j) *s_at(i, j) = acc[i][j] * gn[j];
     __syncthreads();
     if (WRITE_SCORES) {
-      for (int e = t; e < BM * BN; e += THREADS) {
+      for (int e = t; e < BM * BN; e += S_THREADS) {
         const int r = e / BN, c = e - r * BN;
         if (m0 + r < Q && n0 + c < N)
           scores_out[static_cast<size_t>(m0 + r) * N + n0 + c] =
               Ss[r * S_LD + c] * __ldg(q_inv_norm + m0 + r);
       }
     } else if (t < BM) {
+      TopKList<KMAX, int32_t> top;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        top.v[j] = Lv[j * BM + t];
+        top.i[j] = Li[j * BM + t];
+      }
       const int n_valid = min(BN, N - n0);
       const float* s = Ss + t * S_LD;
       for (int c = 0; c < n_valid; ++c) top.push_ordered(s[c], n0 + c);
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        Lv[j * BM + t] = top.v[j];
+        Li[j * BM + t] = top.i[j];
+      }
     }
   }
   if (!WRITE_SCORES && rank == 0 && t < BM && m0 + t < Q) {
@@ -232,8 +291,8 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
 #pragma unroll
     for (int j = 0; j < KMAX; ++j)
       if (j < k) {
-        part_val[o + j] = top.v[j];
-        part_idx[o + j] = top.i[j];
+        part_val[o + j] = Lv[j * BM + t];
+        part_idx[o + j] = Li[j * BM + t];
       }
   }
   // (SPLIT == 2: every DSMEM store precedes the last cluster barrier, so either CTA may exit now)
@@ -514,15 +573,16 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
     if (k <= 4) IRR_LAUNCH_BIG(4); else IRR_LAUNCH_BIG(16);
 #undef IRR_LAUNCH_BIG
   } else {
-    // too few CTAs to give every SM one: split K over a cluster of two CTAs (same bits, see the kernel)
-    const bool split = grid <= num_sms() && split_k_enabled();
+    // fewer CTAs than half the resident slots (three per SM): split K over a cluster of two CTAs
+    // (same bits, see the kernel) — 10k rows: 157 tiles -> 314 CTAs on 444 slots
+    const bool split = 2 * grid <= 3 * num_sms() && split_k_enabled();
 #define IRR_LAUNCH_SMALL(KM, SP)                                                                  \
   do {                                                                                            \
     auto kern = cosine_topk_f32_kernel<KM, false, SP>;                                            \
     IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
     cudaLaunchConfig_t cfg = {};                                                                  \
     cfg.gridDim = dim3(grid * SP);                                                                \
-    cfg.blockDim = dim3(THREADS);                                                                 \
+    cfg.blockDim = dim3(S_THREADS);                                                               \
     cfg.dynamicSmemBytes = SMEM_BYTES;                                                            \
     cfg.stream = st;                                                                              \
     cudaLaunchAttribute at[1];                                                                    \
@@ -567,7 +627,7 @@ irr_status f32_cosine_scores(const void* q, const void* g, const float* g_inv_no
   const Plan p = make_plan(Q, N);
   auto kern = cosine_topk_f32_kernel<4, true, 1>;
   IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  kern<<<p.m_tiles * p.n_chunks, THREADS, SMEM_BYTES, st>>>(
+  kern<<<p.m_tiles * p.n_chunks, S_THREADS, SMEM_BYTES, st>>>(
       static_cast<const float*>(q), static_cast<const float*>(g), g_inv_norm, static_cast<int>(Q),
       static_cast<int>(N), D, 1, p.m_tiles, p.n_tiles, p.tiles_per_chunk, nullptr, nullptr,
       q_inv_norm, out_scores);
