@@ -1014,11 +1014,13 @@ __global__ void __launch_bounds__(256) zero_words_kernel(uint32_t* __restrict__ 
 // straddles into the next wave, where its late units stream it AGAIN — one wave after the first
 // pass, and a wave of long chunks moves more bytes than L2 holds: at 4096 queries (16 pairs on 74
 // clusters, 4.6 chunks per wave of 53 tiles = 193 MB) every fifth chunk was read twice, 3.77 GB of
-// DRAM reads for 3.08 GB of gallery.  From 12 pairs on (a straddler is >= 15 % of a wave) the
+// DRAM reads for 3.08 GB of gallery.  (a) From 12 pairs on (a straddler is >= 15 % of a wave) the
 // chunks are therefore kept short enough that a wave's tiles stay in L2 until the late units
-// come by: 8 tiles at 4096 x 1536 -> 3.12 GB, same kernel time (profiles/r02_notes.md).
+// come by: 8 tiles at 4096 x 1536 -> 3.12 GB, same kernel time (profiles/r02_notes.md).  (b) Only
+// for k <= 4: every unit restarts its rows' lists, which is free for three entries and was
+// measured 14 % slower for config 5's k = 10 (16-entry lists, 611 instead of 111 chunks).
 constexpr size_t WAVE_L2_BUDGET = 32u << 20;   // a quarter of the 126 MB L2
-Plan make_plan_pair(int64_t Q, int64_t N, int32_t D) {
+Plan make_plan_pair(int64_t Q, int64_t N, int32_t D, int32_t k) {
   Plan p;
   const int clusters = num_sms() / 2;
   p.m_tiles = static_cast<int>((Q + 2 * BLOCK_M - 1) / (2 * BLOCK_M));  // pairs of query tiles
@@ -1027,7 +1029,11 @@ Plan make_plan_pair(int64_t Q, int64_t N, int32_t D) {
   int best_tpc = 1;
   double best_cost = 1e300;
   int max_tpc = p.n_tiles < 64 ? p.n_tiles : 64;
-  if (p.m_tiles >= 12) {
+  // (c) only for launches long enough to run at the power cap (about 5 ms of tile stream and up):
+  // the DRAM reads saved are energy, not time — uncapped (a 1 ms launch on one of 8 GPUs) the
+  // extra units cost 1.5 % and save nothing.
+  const bool long_launch = 1ll * p.n_tiles * p.m_tiles * D >= 512ll * clusters * 1536;
+  if (p.m_tiles >= 12 && k <= 4 && long_launch) {
     const size_t chunks_per_wave = static_cast<size_t>((clusters + p.m_tiles - 1) / p.m_tiles);
     const size_t tile_bytes = static_cast<size_t>(BLOCK_N) * static_cast<size_t>(D > 0 ? D : 1) * 2;
     const int cap = static_cast<int>(WAVE_L2_BUDGET / (chunks_per_wave * tile_bytes));
@@ -1261,7 +1267,7 @@ size_t bf16_topk_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t k) {
   // the caller may or may not pass cached norms: size for the larger of the two plans
   size_t parts = 0;
   for (int cached = 0; cached < 2; ++cached) {
-    const Plan p = use_pair(Q, cached) ? make_plan_pair(Q, N, D) : make_plan(Q, N);
+    const Plan p = use_pair(Q, cached) ? make_plan_pair(Q, N, D, k) : make_plan(Q, N);
     const size_t n = static_cast<size_t>(p.n_chunks) * Q * k;
     if (n > parts) parts = n;
   }
@@ -1280,7 +1286,7 @@ irr_status bf16_cosine_topk(const void* q, const void* g, const float* g_inv_nor
   if (ws_bytes < bf16_topk_workspace_bytes(Q, N, D, k)) return IRR_ERR_WORKSPACE_TOO_SMALL;
   const bool cached = g_inv_norm != nullptr;
   const bool pair = use_pair(Q, cached);
-  const Plan p = pair ? make_plan_pair(Q, N, D) : make_plan(Q, N);
+  const Plan p = pair ? make_plan_pair(Q, N, D, k) : make_plan(Q, N);
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* gin_ws = reinterpret_cast<float*>(w);
   w += align_up(static_cast<size_t>(N) * 4, 256);

@@ -537,12 +537,14 @@ def test_dispatch_regime_sweep(Q, D, N):
         assert (unc.values[:, 0] == unc.values[:, 1]).all()
 
 
-def test_many_pairs_short_chunks():
-    """Thirteen query-tile pairs (Q = 3100, ragged last pair) over 235 gallery tiles: from twelve
-    pairs on make_plan_pair keeps chunks short (here 7 tiles -> 34 chunks, 442 units in six waves
-    on 74 clusters, every wave ending in a chunk that straddles into the next), cached norms and
-    the paced in-kernel producers; 34 partial lists per query through the merge.  Against the fp64
-    oracle of train/train_efficient_cos_con_ce_loss.py:273-276 on a gallery with duplicate rows."""
+def test_thirteen_pairs_chunks_straddle_waves():
+    """Thirteen query-tile pairs (Q = 3100, ragged last pair) over 235 gallery tiles: 17 chunks x 13
+    pairs = 221 units in three waves on 74 clusters, every wave ending in a chunk that straddles
+    into the next; cached norms and the paced in-kernel producers; 17 partial lists per query
+    through the merge.  (The planner's short chunks for long launches — 8 tiles, 489 partial lists
+    at 4096 x 1M — are what test_headline_1m_planted[4096] and bench.py's self-check run.)
+    Against the fp64 oracle of train/train_efficient_cos_con_ce_loss.py:273-276 on a gallery with
+    duplicate rows."""
     Q, N, D = 3100, 60_013, 1536
     q, gal = synthetic.tied_gallery(N, D, Q, seed=31, dtype=torch.bfloat16)
     qd, gd = q.cuda(), gal.cuda()

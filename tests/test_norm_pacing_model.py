@@ -16,14 +16,14 @@ BLOCK_M, BLOCK_N, OCTETS = 128, 256, 32
 SMS = 148
 
 
-def plan_pair(Q, N, D=1536):
-    """make_plan_pair(): chunks short enough that a wave's tiles stay in L2 from 12 pairs on"""
+def plan_pair(Q, N, D=1536, k=3):
+    """make_plan_pair(): chunks short enough that a wave's tiles stay in L2 from 12 pairs on (k <= 4)"""
     clusters = SMS // 2
     m_pairs = (Q + 2 * BLOCK_M - 1) // (2 * BLOCK_M)
     n_tiles = max((N + BLOCK_N - 1) // BLOCK_N, 1)
     best, best_cost = 1, 1e300
     max_tpc = min(n_tiles, 64)
-    if m_pairs >= 12:
+    if m_pairs >= 12 and k <= 4 and n_tiles * m_pairs * D >= 512 * clusters * 1536:
         chunks_per_wave = (clusters + m_pairs - 1) // m_pairs
         max_tpc = min(max_tpc, max((32 << 20) // (chunks_per_wave * BLOCK_N * D * 2), 4))
     for tpc in range(1, max_tpc + 1):
@@ -141,8 +141,8 @@ def test_workspace_covers_the_pair_plan_and_the_tile_counters(Q, N):
     kernel's plan needs: cached norms + two partial-list arrays + row floors + per-tile counters."""
     from imageretrievalresearch_b200 import _lib
     lib = _lib.load()
-    m_pairs, n_tiles, tpc, n_chunks, _ = plan_pair(Q, N)
     for k in (1, 3, 10, 16):
+        m_pairs, n_tiles, tpc, n_chunks, _ = plan_pair(Q, N, 1536, k)
         parts = n_chunks * Q * k
         need = N * 4 + 2 * parts * 4 + Q * 4 + n_tiles * 4
         got = lib.irr_cosine_topk_workspace_bytes(Q, N, 1536, k, _lib.IRR_BF16)
