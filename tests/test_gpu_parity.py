@@ -763,6 +763,32 @@ def test_large_k_select(dtype, Q, N, D, k):
     assert (res.indices[:, 0] < res.indices[:, 1]).all() or N < 4
 
 
+@pytest.mark.parametrize("N,copies", [(6000, 2500), (20_000, 1500), (40_000, 3000)])
+def test_large_k_crowded_score_bin(N, copies):
+    """k = 150 where the k-th best score sits among thousands of EXACTLY equal scores (copies of one
+    gallery row): the histogram form of topk_select (short rows) finds more keys in the k-th
+    score's bin than its buffer holds and falls back to the streaming form (N = 40 000 takes the
+    streaming form directly); either way the equal scores must come back in ascending index order
+    (ipynb:238: torch.topk(sim, k=150); ties -> lower gallery index)."""
+    D, Q, k = 256, 9, 150
+    g = torch.Generator().manual_seed(N)
+    gal = torch.randn(N, D, generator=g)
+    q = torch.randn(Q, D, generator=g)
+    where = torch.randperm(N, generator=g)[:copies].sort().values
+    gal[where] = q.sum(dim=0) * 0.7   # one row, `copies` times: cos ~ 1/3 with every query, far
+    res = irr.cosine_topk(q.cuda(), gal.cuda(), k)          # above the random rows' ~0.2 at most
+    check_topk(res, q, gal, k, 2e-6, relative=False)
+    vals, idx = res.values.cpu(), res.indices.cpu()
+    for r in range(Q):
+        # a few random rows may beat the copies; the rest of the list runs through the block of
+        # equal scores and must hold the LOWEST copies, ascending, with bit-identical scores
+        dup = torch.isin(idx[r], where)
+        mine = idx[r][dup]
+        assert mine.numel() >= 50 and bool(dup[-1])
+        assert torch.equal(mine, where[: mine.numel()])
+        assert (vals[r][dup] == vals[r][dup][0]).all()
+
+
 def test_large_k_query_blocking(monkeypatch):
     """N large enough that the score block holds fewer rows than Q (several blocks)."""
     q, gal, pos = synthetic.planted_gallery(1_200_000, 64, 300, 3, seed=12, dtype=torch.bfloat16)
