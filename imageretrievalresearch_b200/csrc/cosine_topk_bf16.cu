@@ -189,9 +189,17 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float* gn, i
     }
     if (WRITE_SCORES) {
       if (row < Q) {
+        float* dst = scores_out + static_cast<size_t>(row) * N + n0 + c;
+        if ((N & 3) == 0 && c + 32 <= n_valid) {   // 16-byte stores (n0 and c are multiples of 32)
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c + j < n_valid) scores_out[static_cast<size_t>(row) * N + n0 + c + j] = v[j] * qn;
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) =
+                make_float4(v[j] * qn, v[j + 1] * qn, v[j + 2] * qn, v[j + 3] * qn);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c + j < n_valid) dst[j] = v[j] * qn;
+        }
       }
     } else {
       if (c + 32 > n_valid) {
