@@ -412,7 +412,9 @@ cosine_topk_f32_big_kernel(const float* __restrict__ q, const float* __restrict_
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int f = t + i * THREADS;
-        const int row = f >> 2, kq = (f & 3) * 4;
+        // k rows 8..15 of a slab keep their columns XOR 8: the four k-quads of a warp's 32 scalar
+        // stores (row stride 132 = 4 mod 32) then cover all 32 banks instead of colliding in pairs
+        const int kq = (f & 3) * 4, row = (f >> 2) ^ (kq & 8);
         a[(kq + 0) * GA_LD + row] = ra[i].x;
         a[(kq + 1) * GA_LD + row] = ra[i].y;
         a[(kq + 2) * GA_LD + row] = ra[i].z;
@@ -431,14 +433,13 @@ cosine_topk_f32_big_kernel(const float* __restrict__ q, const float* __restrict_
     for (int ks = 0; ks < num_ks; ++ks) {
       const int buf = ks & 1;
       if (ks + 1 < num_ks) gload(ks + 1);
-      const float* a = As + buf * BK * GA_LD + ty * 4;
-      const float* b = Bs + buf * BK * GB_LD + tx * 4;
 #pragma unroll
       for (int kk = 0; kk < BK; ++kk) {
-        const float4 a0 = *reinterpret_cast<const float4*>(a + kk * GA_LD);
-        const float4 a1 = *reinterpret_cast<const float4*>(a + kk * GA_LD + 64);
-        const float4 b0 = *reinterpret_cast<const float4*>(b + kk * GB_LD);
-        const float4 b1 = *reinterpret_cast<const float4*>(b + kk * GB_LD + 64);
+        const int sw = kk & 8;   // (compile-time per unrolled step)
+        const float4 a0 = *reinterpret_cast<const float4*>(As + buf * BK * GA_LD + kk * GA_LD + ((ty * 4) ^ sw));
+        const float4 a1 = *reinterpret_cast<const float4*>(As + buf * BK * GA_LD + kk * GA_LD + 64 + ((ty * 4) ^ sw));
+        const float4 b0 = *reinterpret_cast<const float4*>(Bs + buf * BK * GB_LD + kk * GB_LD + ((tx * 4) ^ sw));
+        const float4 b1 = *reinterpret_cast<const float4*>(Bs + buf * BK * GB_LD + kk * GB_LD + 64 + ((tx * 4) ^ sw));
         const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
                               make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
