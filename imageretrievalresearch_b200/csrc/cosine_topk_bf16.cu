@@ -68,6 +68,7 @@ struct Knobs {
   int norm_ahead;            // IRR_NORM_AHEAD: tiles the producers may run ahead (negative = unpaced)
   bool fused_pair;           // IRR_FUSED_PAIR=0: no fused norms in the pair kernel (pre-pass instead)
   bool pdl;                  // IRR_PDL=0: no programmatic dependent launches along a search's kernels
+  bool m64;                  // IRR_M64=0: 128-row MMAs also for up to 64 queries
 };
 const Knobs& knobs() {
   static const Knobs k = []() {
@@ -82,6 +83,7 @@ const Knobs& knobs() {
     r.norm_ahead = num("IRR_NORM_AHEAD", 1);   // one tile: same speed as two, 4.59 instead of 5.44 GB of DRAM reads
     r.fused_pair = !flag("IRR_FUSED_PAIR", '0');
     r.pdl = !flag("IRR_PDL", '0');
+    r.m64 = !flag("IRR_M64", '0');
     return r;
   }();
   return k;
@@ -310,7 +312,7 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         int tiles_per_chunk, int n_chunks, float* __restrict__ part_val,
                         int32_t* __restrict__ part_idx, float* __restrict__ scores_out,
                         uint64_t g_policy, float eps, int tail_tile, int tail_bytes,
-                        uint32_t* __restrict__ row_floor, int is_f16) {
+                        uint32_t* __restrict__ row_floor, int is_f16, int mma_m) {
   using G = SC;
   constexpr int STAGES = G::STAGES;
   constexpr int ACC = G::ACC;
@@ -395,7 +397,10 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_16(BLOCK_M, BLOCK_N, is_f16 != 0);
+    // mma_m = 64 for up to 64 queries: half the multipliers of the 128-row datapath stay idle —
+    // same MMA time (the kernel is HBM-bound there anyway), less energy, and a sustained loop of
+    // small batches runs at the power cap (profiles/r02_notes.md)
+    const uint32_t idesc = umma_idesc_16(mma_m, BLOCK_N, is_f16 != 0);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t it = 0;  // accumulator tiles issued by this CTA
@@ -476,7 +481,9 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ===================== epilogue: scale + running top-k =====================
     const int ew = warp - EPI_WARP0;          // == warp % 4: TMEM lane quarter this warp may read
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
-    const int row_in_tile = ew * 32 + lane;
+    // accumulator rows -> TMEM lanes: M = 128: row r in lane r; M = 64: row r in lane
+    // 32 (r / 16) + r % 16 (every warp's lane quarter holds 16 rows, its lanes 16-31 nothing)
+    const int row_in_tile = mma_m == 64 ? (lane < 16 ? ew * 16 + lane : BLOCK_M) : ew * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
     TopKList<KMAX, int32_t> top;
     uint32_t it = 0;
@@ -1261,7 +1268,8 @@ irr_status launch(const QueryMaps& qm, const CUtensorMap& tg, const float* gin, 
   const cudaError_t e = cudaLaunchKernelEx(
       &cfg, kern, qm.full, qm.tail, tg, gin, qin, static_cast<int>(Q), static_cast<int>(N), num_kb,
       static_cast<int>(k), p.m_tiles, p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi, scores,
-      g_policy, eps, qm.tail_tile, qm.tail_bytes, row_floor, f16 ? 1 : 0);
+      g_policy, eps, qm.tail_tile, qm.tail_bytes, row_floor, f16 ? 1 : 0,
+      (Q <= 64 && p.m_tiles == 1 && knobs().m64) ? 64 : BLOCK_M);
   if (!WS) profile_mark_stop(st);
   if (e != cudaSuccess) return static_cast<irr_status>(static_cast<int>(e));
   return IRR_OK;
