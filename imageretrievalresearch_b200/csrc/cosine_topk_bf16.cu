@@ -397,15 +397,19 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // mma_m = 64 for up to 64 queries: half the multipliers of the 128-row datapath stay idle —
+    // mma_m = 64 allows 64-row MMAs for query tiles of up to 64 rows: half the multipliers of the 128-row datapath stay idle —
     // same MMA time (the kernel is HBM-bound there anyway), less energy, and a sustained loop of
     // small batches runs at the power cap (profiles/r02_notes.md)
-    const uint32_t idesc = umma_idesc_16(mma_m, BLOCK_N, is_f16 != 0);
+    const uint32_t idesc_full = umma_idesc_16(BLOCK_M, BLOCK_N, is_f16 != 0);
+    const uint32_t idesc_half = umma_idesc_16(64, BLOCK_N, is_f16 != 0);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t it = 0;  // accumulator tiles issued by this CTA
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int chunk = u / m_tiles;
+      // a query tile with at most 64 rows (the only tile of a small batch, or a ragged last one)
+      const bool half = mma_m == 64 && Q - (u - chunk * m_tiles) * BLOCK_M <= 64;
+      const uint32_t idesc = half ? idesc_half : idesc_full;
       const int t0 = chunk * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
       for (int t = t0; t < t1; ++t, ++it) {
@@ -483,7 +487,6 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
     // accumulator rows -> TMEM lanes: M = 128: row r in lane r; M = 64: row r in lane
     // 32 (r / 16) + r % 16 (every warp's lane quarter holds 16 rows, its lanes 16-31 nothing)
-    const int row_in_tile = mma_m == 64 ? (lane < 16 ? ew * 16 + lane : BLOCK_M) : ew * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
     TopKList<KMAX, int32_t> top;
     uint32_t it = 0;
@@ -491,7 +494,10 @@ cosine_topk_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int chunk = u / m_tiles, mt = u - chunk * m_tiles;
       const int t0 = chunk * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, n_tiles);
-      const int row = mt * BLOCK_M + row_in_tile;
+      const bool half = mma_m == 64 && Q - mt * BLOCK_M <= 64;   // same rule as the MMA issuer
+      const int row_in_tile = half ? (lane < 16 ? ew * 16 + lane : BLOCK_M) : ew * 32 + lane;
+      // (a lane without a row gets a row index past the tile, hence >= Q: a closed list)
+      const int row = half && lane >= 16 ? Q : mt * BLOCK_M + row_in_tile;
       top.reset();
       // rows past the last query hold whatever the A stage held: their list starts closed (a NaN
       // k-th entry admits nothing), so they never drag their warp into the insert path
@@ -1269,7 +1275,7 @@ irr_status launch(const QueryMaps& qm, const CUtensorMap& tg, const float* gin, 
       &cfg, kern, qm.full, qm.tail, tg, gin, qin, static_cast<int>(Q), static_cast<int>(N), num_kb,
       static_cast<int>(k), p.m_tiles, p.n_tiles, p.tiles_per_chunk, p.n_chunks, pv, pi, scores,
       g_policy, eps, qm.tail_tile, qm.tail_bytes, row_floor, f16 ? 1 : 0,
-      (Q <= 64 && p.m_tiles == 1 && knobs().m64) ? 64 : BLOCK_M);
+      knobs().m64 ? 64 : BLOCK_M);
   if (!WS) profile_mark_stop(st);
   if (e != cudaSuccess) return static_cast<irr_status>(static_cast<int>(e));
   return IRR_OK;
