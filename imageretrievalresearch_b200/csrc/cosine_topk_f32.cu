@@ -153,17 +153,19 @@ cosine_topk_f32_kernel(const float* __restrict__ q, const float* __restrict__ g,
     };
     zero_acc();
 
-    // stage K-slab ks (16 k of the 64 query rows and of the tile's 128 gallery rows) into ring slot
+    // stage K-slab ks (16 k of the 64 query rows and of the tile's 64 gallery rows) into ring slot
     auto issue = [&](int ks, int slot) {
       const int kk = ks * BK;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int f = t + i * S_THREADS;
         const int row = f >> 2, kq = (f & 3) * 4;
-        cp_async16(as_u32 + static_cast<uint32_t>((slot * BM + row) * ROW_LD + kq) * 4u, a_src[i] + kk,
-                   (a_ok[i] && kk + kq < D) ? 16u : 0u);
-        cp_async16(bs_u32 + static_cast<uint32_t>((slot * BN + row) * ROW_LD + kq) * 4u, b_src[i] + kk,
-                   (b_ok[i] && kk + kq < D) ? 16u : 0u);
+        // (a zero-filled piece — row or k past the end — still names a valid address)
+        const bool a_in = a_ok[i] && kk + kq < D, b_in = b_ok[i] && kk + kq < D;
+        cp_async16(as_u32 + static_cast<uint32_t>((slot * BM + row) * ROW_LD + kq) * 4u,
+                   a_in ? a_src[i] + kk : q, a_in ? 16u : 0u);
+        cp_async16(bs_u32 + static_cast<uint32_t>((slot * BN + row) * ROW_LD + kq) * 4u,
+                   b_in ? b_src[i] + kk : g, b_in ? 16u : 0u);
       }
     };
     // K-slabs [ks0, ks1) into acc (ascending k; slab ks sits in ring slot (ks - ks0) % ST)
