@@ -152,7 +152,12 @@ topk_select_kernel(const float* __restrict__ scores, int64_t N, int k, int64_t i
       }
     }
     __syncthreads();
-    if (count > SEL_FLUSH_AT || base + SEL_CHUNK >= N) {
+    // every thread takes its decision from the SAME count: without the second barrier a thread
+    // that is late reading it could see the appends of threads already in the next chunk, flush
+    // alone and desynchronise the block (a lost candidate once in ~10^3 long rows)
+    const int appended = count;
+    __syncthreads();
+    if (appended > SEL_FLUSH_AT || base + SEL_CHUNK >= N) {
       sort_keys_desc(keys);
       for (int i = SEL_BEST + threadIdx.x; i < SEL_KEYS; i += SEL_THREADS) keys[i] = 0ull;
       if (threadIdx.x == 0) count = 0;

@@ -1205,3 +1205,16 @@ def test_training_step_composition():
     assert abs(got.item() - want.item()) <= LOSS_REL * abs(want.item())
     for a, b in zip(fc, fr):
         assert rel(a.grad.cpu(), b.grad) < GRAD_REL
+
+
+def test_randomised_parity_stress():
+    """scripts/stress_parity.py for a quarter of a minute: random (Q, N, D, k, dtype) searches,
+    cached and uncached, duplicates in every gallery, against a torch fp64 scan on the device.  (A
+    longer run of this script found the flush-decision race of the streaming large-k selection:
+    one lost candidate in about a thousand long rows.)"""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "scripts", "stress_parity.py"), "15", "7"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().splitlines()[-1].startswith("ok:"), r.stdout[-2000:] + r.stderr[-2000:]
