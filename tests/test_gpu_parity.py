@@ -1212,6 +1212,7 @@ def test_randomised_parity_stress():
     cached and uncached, duplicates in every gallery, against a torch fp64 scan on the device.  (A
     longer run of this script found the flush-decision race of the streaming large-k selection:
     one lost candidate in about a thousand long rows.)"""
+    import os
     import subprocess
     import sys as _sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
