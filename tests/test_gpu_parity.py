@@ -1219,3 +1219,16 @@ def test_randomised_parity_stress():
     r = subprocess.run([_sys.executable, os.path.join(root, "scripts", "stress_parity.py"), "15", "7"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().splitlines()[-1].startswith("ok:"), r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_randomised_loss_stress():
+    """scripts/stress_losses.py for ten seconds: random (B, D, dtype, margin, reduction, weights)
+    fused forward+backward against torch fp64 autograd of utils/contrastive_loss.py:56-61 and
+    CosineEmbeddingLoss, and bit-identical results from repeated launches."""
+    import os
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "scripts", "stress_losses.py"), "10", "5"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().splitlines()[-1].startswith("ok:"), r.stdout[-2000:] + r.stderr[-2000:]
