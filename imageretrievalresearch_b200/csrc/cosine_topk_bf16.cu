@@ -9,7 +9,9 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles of Q (128 x 64) and G (256 x 64),
 //               128-byte swizzle, into a 4-stage shared-memory ring (48 KB per stage)
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256, K=16) x4 per stage,
-//               fp32 accumulators in TMEM, two accumulator stages (2 x 256 of the 512 columns)
+//               fp32 accumulators in TMEM, two accumulator stages (2 x 256 of the 512 columns);
+//               M=64 for a query tile of at most 64 rows (the padding rows of a 128-row MMA cost
+//               energy, and even the HBM-bound searches run at the power cap when sustained)
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue: tcgen05.ld the accumulator (thread = query row, 32 columns at a time),
 //               scale by 1/max(|g|,eps), keep a running sorted top-k per row in registers.
