@@ -1103,18 +1103,6 @@ int pair_norm_mode(bool cached, int m_pairs) {
   return knobs().fused_pair ? NORMS_FUSED : NORMS_CACHED;   // CACHED here = streaming pre-pass first
 }
 
-// cudaFuncSetAttribute once per (kernel instantiation, device), not once per call
-bool attr_needed(std::atomic<uint64_t>& done) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-  return (done.load(std::memory_order_relaxed) >> dev & 1ull) == 0;
-}
-void attr_set(std::atomic<uint64_t>& done) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64)
-    done.fetch_or(1ull << dev, std::memory_order_relaxed);
-}
-
 // NORMS_PRODUCERS: gin is the (not yet filled) fp32[N] buffer the in-kernel producers write and the
 // epilogues read; tile_done is the zeroed per-tile row counter array.  That variant's epilogues
 // wait for producers in OTHER CTAs, so it is launched cooperatively: the driver either makes the

@@ -566,8 +566,12 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
 #define IRR_LAUNCH_BIG(KM)                                                                        \
   do {                                                                                            \
     auto kern = cosine_topk_f32_big_kernel<KM, false>;                                            \
-    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                      big_smem_bytes<KM>()));                                     \
+    static std::atomic<uint64_t> attr_done{0};                                                    \
+    if (attr_needed(attr_done)) {                                                                 \
+      IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                        big_smem_bytes<KM>()));                                   \
+      attr_set(attr_done);                                                                        \
+    }                                                                                             \
     kern<<<grid, THREADS, big_smem_bytes<KM>(), st>>>(                                            \
         static_cast<const float*>(q), static_cast<const float*>(g), gin, static_cast<int>(Q),     \
         static_cast<int>(N), D, k, p.m_tiles, p.n_tiles, p.tiles_per_chunk, pv, pi, nullptr,      \
@@ -582,7 +586,11 @@ irr_status f32_cosine_topk(const void* q, const void* g, const float* g_inv_norm
 #define IRR_LAUNCH_SMALL(KM, SP)                                                                  \
   do {                                                                                            \
     auto kern = cosine_topk_f32_kernel<KM, false, SP>;                                            \
-    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+    static std::atomic<uint64_t> attr_done{0};                                                    \
+    if (attr_needed(attr_done)) {                                                                 \
+      IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+      attr_set(attr_done);                                                                        \
+    }                                                                                             \
     cudaLaunchConfig_t cfg = {};                                                                  \
     cfg.gridDim = dim3(grid * SP);                                                                \
     cfg.blockDim = dim3(S_THREADS);                                                               \

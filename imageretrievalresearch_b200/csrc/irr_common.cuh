@@ -6,6 +6,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -43,6 +44,19 @@ inline int dtype_bytes(irr_dtype dt) { return dt == IRR_F32 ? 4 : 2; }
 int num_sms();
 // compute capability major*10+minor of the current device, 0 if none
 int device_cc();
+
+// cudaFuncSetAttribute once per (kernel instantiation, device), not once per call: one bit per
+// device in a function-local static
+inline bool attr_needed(std::atomic<uint64_t>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  return (done.load(std::memory_order_relaxed) >> dev & 1ull) == 0;
+}
+inline void attr_set(std::atomic<uint64_t>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64)
+    done.fetch_or(1ull << dev, std::memory_order_relaxed);
+}
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
