@@ -176,8 +176,12 @@ irr_status avgpool_fwd(const void* fm, int in_dt, int64_t rows, int32_t hw, void
 #define IRR_POOL(I, O)                                                                              \
   do {                                                                                              \
     auto kern = avgpool_fwd_kernel<I, O>;                                                           \
-    IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                      static_cast<int>(smem)));                                     \
+    static std::atomic<uint64_t> attr_done{0};   /* the budget, once per instantiation and device */ \
+    if (attr_needed(attr_done)) {                                                                   \
+      IRR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                        static_cast<int>(POOL_SMEM_MAX)));                          \
+      attr_set(attr_done);                                                                          \
+    }                                                                                               \
     kern<<<grid, POOL_ROWS, smem, st>>>(fm, rows, hw, rpc, out, inv);                               \
   } while (0)
   if (out_dt == IRR_F32) {
